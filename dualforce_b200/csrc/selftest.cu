@@ -1,0 +1,417 @@
+// Standalone device self-test of the C-ABI library (no torch): every kernel against a naive CUDA
+// reference on the same inputs.  One sub-command per process so a faulting kernel cannot poison the rest:
+//   selftest gemm <cta_group> <epilogue> <M> <N> <K> [iters]
+//   selftest attn <B> <Sq> <Skv> <H> [iters]
+//   selftest ln   <L> <d> <affine 0|1> <modulate 0|1>
+//   selftest rr   <L> <d> <rope_mode>
+//   selftest merge <parts> <rows> <H>
+// Exit code 0 = within tolerance.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/mova_b200.h"
+
+#define CK(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) {                                                                    \
+      printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_));   \
+      exit(3);                                                                                  \
+    }                                                                                           \
+  } while (0)
+#define CKMV(x)                                                              \
+  do {                                                                       \
+    int r_ = (x);                                                            \
+    if (r_ != 0) {                                                           \
+      printf("mova_b200 error %d: %s\n", r_, mova_b200_last_error());        \
+      exit(4);                                                               \
+    }                                                                        \
+  } while (0)
+
+static uint64_t g_seed = 0x9E3779B97F4A7C15ull;
+static inline float frand() {  // uniform in [-1, 1)
+  g_seed = g_seed * 6364136223846793005ull + 1442695040888963407ull;
+  return static_cast<float>((g_seed >> 40) & 0xFFFFFF) / 8388608.0f - 1.0f;
+}
+static inline float bf16_round(float f) { return __bfloat162float(__float2bfloat16(f)); }
+
+static __nv_bfloat16* dev_bf16(size_t n, float scale, std::vector<float>* host = nullptr) {
+  std::vector<__nv_bfloat16> h(n);
+  if (host) host->resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    h[i] = __float2bfloat16(frand() * scale);
+    if (host) (*host)[i] = __bfloat162float(h[i]);
+  }
+  __nv_bfloat16* d;
+  CK(cudaMalloc(&d, n * 2));
+  CK(cudaMemcpy(d, h.data(), n * 2, cudaMemcpyHostToDevice));
+  return d;
+}
+static float* dev_f32(size_t n, float scale, float offset = 0.f, std::vector<float>* host = nullptr) {
+  std::vector<float> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = frand() * scale + offset;
+  if (host) *host = h;
+  float* d;
+  CK(cudaMalloc(&d, n * 4));
+  CK(cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice));
+  return d;
+}
+
+struct ErrStat {
+  double max_abs = 0, max_ref = 0, sum_sq_err = 0, sum_sq_ref = 0;
+  size_t bad = 0, n = 0;
+  void add(float got, float ref) {
+    const double e = fabs(static_cast<double>(got) - ref);
+    if (!(e == e)) bad++;
+    if (e > max_abs) max_abs = e;
+    if (fabs(ref) > max_ref) max_ref = fabs(ref);
+    sum_sq_err += e * e;
+    sum_sq_ref += static_cast<double>(ref) * ref;
+    n++;
+  }
+  double rel_fro() const { return sqrt(sum_sq_err / (sum_sq_ref + 1e-30)); }
+  bool report(const char* name, double tol_rel_absmax, double tol_fro) const {
+    const double rel = max_abs / (max_ref + 1e-30);
+    const bool ok = bad == 0 && rel <= tol_rel_absmax && rel_fro() <= tol_fro;
+    printf("%-28s n=%zu max_abs_err=%.4g (abs-max %.4g, ratio %.3g) rel_fro=%.3g nan=%zu  -> %s\n", name, n, max_abs,
+           max_ref, rel, rel_fro(), bad, ok ? "OK" : "FAIL");
+    return ok;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// naive references
+// ----------------------------------------------------------------------------------------------
+__global__ void ref_gemm_kernel(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
+                                const __nv_bfloat16* bias, const __nv_bfloat16* R, long long ldr, const float* gate,
+                                float scale, int epi, float* C, int M, int N, int K) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += __bfloat162float(A[m * lda + k]) * __bfloat162float(W[n * ldw + k]);
+  if (bias) acc += __bfloat162float(bias[n]);
+  if (epi == MOVA_EPI_GELU_TANH) {
+    acc = 0.5f * acc * (1.0f + tanhf(0.7978845608028654f * (acc + 0.044715f * acc * acc * acc)));
+  } else if (epi == MOVA_EPI_RESIDUAL) {
+    acc = __bfloat162float(R[m * ldr + n]) + (gate ? gate[n] : 1.0f) * scale * acc;
+  }
+  C[static_cast<long long>(m) * N + n] = acc;
+}
+
+// one thread per (b, h, q row): plain two-pass softmax attention in fp32
+__global__ void ref_attn_kernel(const __nv_bfloat16* q, long long q_bs, long long q_ss, const __nv_bfloat16* k,
+                                long long k_bs, long long k_ss, const __nv_bfloat16* v, long long v_bs, long long v_ss,
+                                float* o, float* lse, int B, int Sq, int Skv, int H, float scale) {
+  const int D = 128;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * H * Sq) return;
+  const int s = idx % Sq;
+  const int h = (idx / Sq) % H;
+  const int b = idx / (static_cast<long long>(Sq) * H);
+  const __nv_bfloat16* qr = q + b * q_bs + s * q_ss + h * D;
+  float qf[128];
+  for (int d = 0; d < D; ++d) qf[d] = __bfloat162float(qr[d]);
+  float m = -INFINITY;
+  for (int j = 0; j < Skv; ++j) {
+    const __nv_bfloat16* kr = k + b * k_bs + j * k_ss + h * D;
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) dot += qf[d] * __bfloat162float(kr[d]);
+    m = fmaxf(m, dot * scale);
+  }
+  float acc[128];
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  float l = 0.f;
+  for (int j = 0; j < Skv; ++j) {
+    const __nv_bfloat16* kr = k + b * k_bs + j * k_ss + h * D;
+    const __nv_bfloat16* vr = v + b * v_bs + j * v_ss + h * D;
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) dot += qf[d] * __bfloat162float(kr[d]);
+    const float p = expf(dot * scale - m);
+    l += p;
+    for (int d = 0; d < D; ++d) acc[d] += p * __bfloat162float(vr[d]);
+  }
+  float* orow = o + ((static_cast<long long>(b) * Sq + s) * H + h) * D;
+  for (int d = 0; d < D; ++d) orow[d] = acc[d] / l;
+  lse[(static_cast<long long>(b) * H + h) * Sq + s] = m + logf(l);
+}
+
+// ----------------------------------------------------------------------------------------------
+static int test_gemm(int argc, char** argv) {
+  if (argc < 7) { printf("usage: gemm cg epi M N K [iters]\n"); return 2; }
+  const int cg = atoi(argv[2]), epi = atoi(argv[3]), M = atoi(argv[4]), N = atoi(argv[5]), K = atoi(argv[6]);
+  const int iters = argc > 7 ? atoi(argv[7]) : 0;
+  const long long lda = K + 8, ldw = K, ldc = N + 16, ldr = N + 8;  // exercise non-trivial strides
+  __nv_bfloat16* A = dev_bf16(static_cast<size_t>(M) * lda, 1.0f);
+  __nv_bfloat16* W = dev_bf16(static_cast<size_t>(N) * ldw, 0.05f);
+  __nv_bfloat16* bias = dev_bf16(N, 0.5f);
+  __nv_bfloat16* R = dev_bf16(static_cast<size_t>(M) * ldr, 1.0f);
+  float* gate = dev_f32(N, 0.5f, 0.2f);
+  __nv_bfloat16* C;
+  CK(cudaMalloc(&C, static_cast<size_t>(M) * ldc * 2));
+  CK(cudaMemset(C, 0x7f, static_cast<size_t>(M) * ldc * 2));
+  float* Cref;
+  CK(cudaMalloc(&Cref, static_cast<size_t>(M) * N * 4));
+  const float scale = 0.75f;
+
+  CKMV(mova_b200_linear(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, R, ldr, gate, scale, cg, nullptr));
+  CK(cudaDeviceSynchronize());
+
+  const bool check = static_cast<double>(M) * N * K <= 3.0e12;
+  bool ok = true;
+  if (check) {
+    ref_gemm_kernel<<<dim3((N + 127) / 128, M), 128>>>(A, lda, W, ldw, bias, R, ldr, gate, scale, epi, Cref, M, N, K);
+    CK(cudaDeviceSynchronize());
+    std::vector<__nv_bfloat16> hC(static_cast<size_t>(M) * ldc);
+    std::vector<float> hR(static_cast<size_t>(M) * N);
+    CK(cudaMemcpy(hC.data(), C, hC.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hR.data(), Cref, hR.size() * 4, cudaMemcpyDeviceToHost));
+    ErrStat st;
+    size_t pad_touched = 0;
+    for (int m = 0; m < M; ++m) {
+      for (int n = 0; n < N; ++n) st.add(__bfloat162float(hC[m * ldc + n]), hR[static_cast<size_t>(m) * N + n]);
+      for (int n = N; n < ldc; ++n) {
+        uint16_t raw;
+        memcpy(&raw, &hC[m * ldc + n], 2);
+        if (raw != 0x7f7f) pad_touched++;
+      }
+    }
+    char name[128];
+    snprintf(name, sizeof(name), "gemm cg%d epi%d %dx%dx%d", cg, epi, M, N, K);
+    ok = st.report(name, 1.0e-2, 6e-3);
+    if (pad_touched) { printf("  padding columns overwritten: %zu\n", pad_touched); ok = false; }
+  }
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i)
+      CKMV(mova_b200_linear(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, R, ldr, gate, scale, cg, nullptr));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i)
+      CKMV(mova_b200_linear(A, lda, W, ldw, bias, C, ldc, M, N, K, epi, R, ldr, gate, scale, cg, nullptr));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    printf("  timing: %.3f ms/iter  %.1f TFLOP/s\n", ms, 2.0 * M * N * K / ms * 1e-9);
+  }
+  return ok ? 0 : 1;
+}
+
+static int test_attn(int argc, char** argv) {
+  if (argc < 6) { printf("usage: attn B Sq Skv H [iters]\n"); return 2; }
+  const int B = atoi(argv[2]), Sq = atoi(argv[3]), Skv = atoi(argv[4]), H = atoi(argv[5]), D = 128;
+  const int iters = argc > 6 ? atoi(argv[6]) : 0;
+  // q,k,v live interleaved in one [B, S, 3*H*D] buffer when Sq == Skv (fused-QKV layout), separate otherwise
+  const bool fused = (Sq == Skv);
+  const long long row = static_cast<long long>(H) * D;
+  __nv_bfloat16 *q, *k, *v;
+  long long q_ss, k_ss, v_ss, q_bs, k_bs, v_bs;
+  if (fused) {
+    __nv_bfloat16* qkv = dev_bf16(static_cast<size_t>(B) * Sq * 3 * row, 1.0f);
+    q = qkv; k = qkv + row; v = qkv + 2 * row;
+    q_ss = k_ss = v_ss = 3 * row;
+    q_bs = k_bs = v_bs = static_cast<long long>(Sq) * 3 * row;
+  } else {
+    q = dev_bf16(static_cast<size_t>(B) * Sq * row, 1.0f);
+    k = dev_bf16(static_cast<size_t>(B) * Skv * row, 1.0f);
+    v = dev_bf16(static_cast<size_t>(B) * Skv * row, 1.0f);
+    q_ss = k_ss = v_ss = row;
+    q_bs = static_cast<long long>(Sq) * row;
+    k_bs = v_bs = static_cast<long long>(Skv) * row;
+  }
+  __nv_bfloat16* o;
+  CK(cudaMalloc(&o, static_cast<size_t>(B) * Sq * row * 2));
+  CK(cudaMemset(o, 0x7f, static_cast<size_t>(B) * Sq * row * 2));
+  float *lse, *oref, *lseref;
+  CK(cudaMalloc(&lse, static_cast<size_t>(B) * H * Sq * 4));
+  CK(cudaMalloc(&oref, static_cast<size_t>(B) * Sq * row * 4));
+  CK(cudaMalloc(&lseref, static_cast<size_t>(B) * H * Sq * 4));
+  const float scale = 1.0f / sqrtf(128.f) * 3.0f;  // sharper than 1/sqrt(D) so the softmax is not flat
+  CKMV(mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row, lse, B,
+                          Sq, Skv, H, D, scale, nullptr));
+  CK(cudaDeviceSynchronize());
+  bool ok = true;
+  if (static_cast<double>(B) * H * Sq * Skv <= 4.0e9) {
+    const long long total = static_cast<long long>(B) * H * Sq;
+    ref_attn_kernel<<<static_cast<unsigned>((total + 63) / 64), 64>>>(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, oref,
+                                                                      lseref, B, Sq, Skv, H, scale);
+    CK(cudaDeviceSynchronize());
+    std::vector<__nv_bfloat16> ho(static_cast<size_t>(B) * Sq * row);
+    std::vector<float> hor(ho.size()), hl(static_cast<size_t>(B) * H * Sq), hlr(hl.size());
+    CK(cudaMemcpy(ho.data(), o, ho.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hor.data(), oref, hor.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hl.data(), lse, hl.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hlr.data(), lseref, hlr.size() * 4, cudaMemcpyDeviceToHost));
+    ErrStat so, sl;
+    for (size_t i = 0; i < ho.size(); ++i) so.add(__bfloat162float(ho[i]), hor[i]);
+    for (size_t i = 0; i < hl.size(); ++i) sl.add(hl[i], hlr[i]);
+    char name[128];
+    snprintf(name, sizeof(name), "attn B%d Sq%d Skv%d H%d", B, Sq, Skv, H);
+    ok = so.report(name, 1.5e-2, 1.0e-2);
+    ok = sl.report("  lse", 1e-3, 1e-3) && ok;
+  }
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i)
+      CKMV(mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
+                              nullptr, B, Sq, Skv, H, D, scale, nullptr));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i)
+      CKMV(mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
+                              nullptr, B, Sq, Skv, H, D, scale, nullptr));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    printf("  timing: %.3f ms/iter  %.1f TFLOP/s\n", ms, 4.0 * B * H * Sq * Skv * D / ms * 1e-9);
+  }
+  return ok ? 0 : 1;
+}
+
+static int test_ln(int argc, char** argv) {
+  if (argc < 6) { printf("usage: ln L d affine modulate\n"); return 2; }
+  const int L = atoi(argv[2]), d = atoi(argv[3]), aff = atoi(argv[4]), mod = atoi(argv[5]);
+  const long long ldx = d + 8, ldy = d;
+  std::vector<float> hx, hw, hb, hsh, hsc;
+  __nv_bfloat16* x = dev_bf16(static_cast<size_t>(L) * ldx, 2.0f, &hx);
+  __nv_bfloat16* w = dev_bf16(d, 1.0f, &hw);
+  __nv_bfloat16* b = dev_bf16(d, 1.0f, &hb);
+  float* sh = dev_f32(d, 0.5f, 0.f, &hsh);
+  float* sc = dev_f32(d, 0.5f, 0.f, &hsc);
+  __nv_bfloat16* y;
+  CK(cudaMalloc(&y, static_cast<size_t>(L) * ldy * 2));
+  const float eps = 1e-6f;
+  CKMV(mova_b200_layernorm(x, ldx, y, ldy, L, d, eps, aff ? w : nullptr, aff ? b : nullptr, mod ? sh : nullptr,
+                           mod ? sc : nullptr, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<__nv_bfloat16> hy(static_cast<size_t>(L) * ldy);
+  CK(cudaMemcpy(hy.data(), y, hy.size() * 2, cudaMemcpyDeviceToHost));
+  ErrStat st;
+  for (int r = 0; r < L; ++r) {
+    double mean = 0, var = 0;
+    for (int i = 0; i < d; ++i) mean += hx[r * ldx + i];
+    mean /= d;
+    for (int i = 0; i < d; ++i) var += (hx[r * ldx + i] - mean) * (hx[r * ldx + i] - mean);
+    var /= d;
+    const double rstd = 1.0 / sqrt(var + eps);
+    for (int i = 0; i < d; ++i) {
+      double v = (hx[r * ldx + i] - mean) * rstd;
+      if (aff) v = v * hw[i] + hb[i];
+      if (mod) v = v * (1.0 + hsc[i]) + hsh[i];
+      st.add(__bfloat162float(hy[r * ldy + i]), static_cast<float>(v));
+    }
+  }
+  char name[128];
+  snprintf(name, sizeof(name), "layernorm L%d d%d aff%d mod%d", L, d, aff, mod);
+  return st.report(name, 4e-3, 3e-3) ? 0 : 1;
+}
+
+static int test_rr(int argc, char** argv) {
+  if (argc < 5) { printf("usage: rr L d rope_mode\n"); return 2; }
+  const int L = atoi(argv[2]), d = atoi(argv[3]), mode = atoi(argv[4]);
+  const long long ldx = 3LL * d;  // as inside a fused qkv buffer
+  std::vector<float> hx, hw, hc, hs;
+  __nv_bfloat16* x = dev_bf16(static_cast<size_t>(L) * ldx, 2.0f, &hx);
+  __nv_bfloat16* w = dev_bf16(d, 1.0f, &hw);
+  const int tw = mode == MOVA_ROPE_HALF ? 128 : 64;
+  float* c = dev_f32(static_cast<size_t>(L) * tw, 1.0f, 0.f, &hc);
+  float* s = dev_f32(static_cast<size_t>(L) * tw, 1.0f, 0.f, &hs);
+  const float eps = 1e-6f;
+  CKMV(mova_b200_rmsnorm_rope(x + d, ldx, L, d, 128, w, eps, c, s, mode, nullptr));  // the "k" slot
+  CK(cudaDeviceSynchronize());
+  std::vector<__nv_bfloat16> hy(static_cast<size_t>(L) * ldx);
+  CK(cudaMemcpy(hy.data(), x, hy.size() * 2, cudaMemcpyDeviceToHost));
+  ErrStat st;
+  size_t untouched_bad = 0;
+  std::vector<double> n(d);
+  for (int r = 0; r < L; ++r) {
+    const float* xr = &hx[r * ldx + d];
+    double ss = 0;
+    for (int i = 0; i < d; ++i) ss += static_cast<double>(xr[i]) * xr[i];
+    const double inv = 1.0 / sqrt(ss / d + eps);
+    for (int i = 0; i < d; ++i) n[i] = xr[i] * inv * hw[i];
+    for (int i = 0; i < d; ++i) {
+      const int hd = i % 128, base = i - hd;
+      double ref = n[i];
+      if (mode == MOVA_ROPE_INTERLEAVED) {
+        const int pr = hd / 2;
+        const double cr = hc[r * 64 + pr], sr = hs[r * 64 + pr];
+        ref = (hd % 2 == 0) ? n[i] * cr - n[i + 1] * sr : n[i - 1] * sr + n[i] * cr;
+      } else if (mode == MOVA_ROPE_HALF) {
+        const double cr = hc[r * 128 + hd], sr = hs[r * 128 + hd];
+        ref = (hd < 64) ? n[i] * cr - n[base + hd + 64] * sr : n[i] * cr + n[base + hd - 64] * sr;
+      }
+      st.add(__bfloat162float(hy[r * ldx + d + i]), static_cast<float>(ref));
+    }
+    for (int i = 0; i < d; ++i) {  // q and v slots must be untouched
+      if (__bfloat162float(hy[r * ldx + i]) != hx[r * ldx + i]) untouched_bad++;
+      if (__bfloat162float(hy[r * ldx + 2 * d + i]) != hx[r * ldx + 2 * d + i]) untouched_bad++;
+    }
+  }
+  char name[128];
+  snprintf(name, sizeof(name), "rmsnorm_rope L%d d%d mode%d", L, d, mode);
+  bool ok = st.report(name, 4e-3, 3e-3);
+  if (untouched_bad) { printf("  neighbours modified: %zu\n", untouched_bad); ok = false; }
+  return ok ? 0 : 1;
+}
+
+static int test_merge(int argc, char** argv) {
+  if (argc < 5) { printf("usage: merge parts rows H\n"); return 2; }
+  const int P = atoi(argv[2]), rows = atoi(argv[3]), H = atoi(argv[4]), D = 128;
+  std::vector<float> ho, hl;
+  __nv_bfloat16* o = dev_bf16(static_cast<size_t>(P) * rows * H * D, 1.0f, &ho);
+  float* l = dev_f32(static_cast<size_t>(P) * H * rows, 3.0f, 0.f, &hl);
+  __nv_bfloat16* out;
+  float* lo;
+  CK(cudaMalloc(&out, static_cast<size_t>(rows) * H * D * 2));
+  CK(cudaMalloc(&lo, static_cast<size_t>(H) * rows * 4));
+  CKMV(mova_b200_lse_merge(o, l, P, out, static_cast<long long>(H) * D, lo, rows, H, D, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<__nv_bfloat16> hout(static_cast<size_t>(rows) * H * D);
+  std::vector<float> hlo(static_cast<size_t>(H) * rows);
+  CK(cudaMemcpy(hout.data(), out, hout.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hlo.data(), lo, hlo.size() * 4, cudaMemcpyDeviceToHost));
+  ErrStat so, sl;
+  for (int r = 0; r < rows; ++r)
+    for (int h = 0; h < H; ++h) {
+      double m = -1e30, den = 0;
+      for (int p = 0; p < P; ++p) m = fmax(m, hl[(static_cast<size_t>(p) * H + h) * rows + r]);
+      for (int p = 0; p < P; ++p) den += exp(hl[(static_cast<size_t>(p) * H + h) * rows + r] - m);
+      sl.add(hlo[static_cast<size_t>(h) * rows + r], static_cast<float>(m + log(den)));
+      for (int dd = 0; dd < D; ++dd) {
+        double acc = 0;
+        for (int p = 0; p < P; ++p)
+          acc += exp(hl[(static_cast<size_t>(p) * H + h) * rows + r] - m) / den *
+                 ho[((static_cast<size_t>(p) * rows + r) * H + h) * D + dd];
+        so.add(__bfloat162float(hout[(static_cast<size_t>(r) * H + h) * D + dd]), static_cast<float>(acc));
+      }
+    }
+  bool ok = so.report("lse_merge out", 5e-3, 4e-3);
+  ok = sl.report("lse_merge lse", 1e-4, 1e-4) && ok;
+  return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { printf("usage: selftest <gemm|attn|ln|rr|merge> ...\n"); return 2; }
+  CKMV(mova_b200_device_check(0));
+  if (!strcmp(argv[1], "gemm")) return test_gemm(argc, argv);
+  if (!strcmp(argv[1], "attn")) return test_attn(argc, argv);
+  if (!strcmp(argv[1], "ln")) return test_ln(argc, argv);
+  if (!strcmp(argv[1], "rr")) return test_rr(argc, argv);
+  if (!strcmp(argv[1], "merge")) return test_merge(argc, argv);
+  printf("unknown test %s\n", argv[1]);
+  return 2;
+}

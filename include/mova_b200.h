@@ -1,0 +1,102 @@
+/*
+ * mova_b200 -- C ABI of the sm_100a kernels behind the MOVA dual-tower DiT denoising-block forward.
+ *
+ * The reference (Jp-17/DualForce == OpenMOSS/MOVA) has no FFI: its hot path is Python nn.Modules whose
+ * GPU work is done by library kernels.  Each entry point below replaces the library call(s) made at the
+ * cited reference lines; the Python host (dualforce_b200/) binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch); nothing is allocated or retained,
+ *   - activations and weights are bf16 (reference model dtype, scripts/inference_single.py:77),
+ *     modulation / RoPE tables / LSE are fp32,
+ *   - strides (ld*) are in ELEMENTS; rows must be 16-byte aligned (ld % 8 == 0 for bf16),
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation,
+ *   - return 0 on success, negative on error; mova_b200_last_error() describes the last failure of
+ *     the calling thread.  There is no CPU fallback: a non-sm_100 device is an error.
+ */
+#ifndef MOVA_B200_H_
+#define MOVA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOVA_B200_ABI_VERSION 1
+
+/* epilogues of mova_b200_linear */
+#define MOVA_EPI_BIAS 0      /* C = A W^T + b                          nn.Linear                          */
+#define MOVA_EPI_GELU_TANH 1 /* C = gelu_tanh(A W^T + b)               wan_video_dit.py:270-271 (ffn.0+1) */
+#define MOVA_EPI_RESIDUAL 2  /* C = R + gate[n] * scale * (A W^T + b)  wan_video_dit.py:254-255,287-290;  */
+                             /*                                        interactionv2.py:535               */
+
+/* RoPE conventions of mova_b200_rmsnorm_rope */
+#define MOVA_ROPE_NONE 0
+#define MOVA_ROPE_INTERLEAVED 1 /* (2i,2i+1) complex pairs, table [L, head_dim/2]  wan_video_dit.py:131-137 */
+#define MOVA_ROPE_HALF 2        /* rotate-half (i, i+hd/2), table [L, head_dim]    interactionv2.py:40-72   */
+
+int mova_b200_abi_version(void);
+const char* mova_b200_last_error(void);
+
+/* 0 if `device` is an sm_100 part the kernels can run on, negative otherwise. */
+int mova_b200_device_check(int device);
+
+/*
+ * nn.Linear with fused epilogue: C[M,N] = epi(A[M,K] . W[N,K]^T + bias[N]).
+ * Replaces cuBLAS GEMM + ATen elementwise at wan_video_dit.py:171-174,218-221,270-271,287-290 and
+ * interactionv2.py:218-221,251,535.  tcgen05 (UMMA 128x256x16 or CTA-pair 256x256x16), TMA-fed,
+ * persistent, fp32 accumulation in TMEM.
+ *   bias      bf16 [N] or NULL
+ *   residual  bf16 [M, ldr] (MOVA_EPI_RESIDUAL only; may alias C)
+ *   gate      fp32 [N] or NULL (=1)           scale: scalar multiplier of the gated branch
+ *   cta_group 1 or 2 (2 = CTA-pair UMMA, M tile 256); 0 = library default
+ */
+int mova_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
+                     int64_t ldc, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
+                     const float* gate, float scale, int cta_group, void* stream);
+
+/*
+ * Non-causal softmax attention, head_dim 128: O = softmax(Q K^T * softmax_scale) V.
+ * Replaces flash_attention() at wan_video_dit.py:58-91 (called from :188, :241, interactionv2.py:250).
+ *   q: [B, Sq, H, 128]  element (b,s,h,d) at q + b*q_bs + s*q_ss + h*128 + d   (same for k, v, o)
+ *   lse: fp32 [B, H, Sq] natural-log-sum-exp of the scaled scores, or NULL
+ */
+int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs, int64_t k_ss,
+                       const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs, int64_t o_ss,
+                       float* lse, int B, int Sq, int Skv, int H, int D, float softmax_scale, void* stream);
+
+/*
+ * Merge `n_parts` partial attention results over disjoint key sets (split-KV / context-parallel v2a):
+ *   o = sum_p exp(lse_p - lse) o_p,  lse = log sum_p exp(lse_p).
+ *   o_parts: bf16 [n_parts, rows, H*D] contiguous, lse_parts: fp32 [n_parts, H, rows]
+ *   out: bf16 [rows, ldo], lse_out fp32 [H, rows] or NULL
+ */
+int mova_b200_lse_merge(const void* o_parts, const float* lse_parts, int n_parts, void* out, int64_t ldo,
+                        float* lse_out, int rows, int H, int D, void* stream);
+
+/*
+ * y = LayerNorm(x) [* ln_w + ln_b] [* (1 + scale) + shift], one pass, fp32 statistics.
+ * Replaces nn.LayerNorm + modulate() at wan_video_dit.py:94-96,267-269,286,289 and y_norm at
+ * interactionv2.py:322,349.   ln_w/ln_b: bf16 [d] or NULL;  shift/scale: fp32 [d] or NULL.
+ */
+int mova_b200_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int L, int d, float eps,
+                        const void* ln_w, const void* ln_b, const float* shift, const float* scale,
+                        void* stream);
+
+/*
+ * In-place x = RoPE(RMSNorm_full(x) * w): RMS over the whole row of d = H*head_dim channels
+ * (torch.nn.RMSNorm(dim), wan_video_dit.py:175-176,181-182; interactionv2.py:222-223,229-230) followed by
+ * the rotary embedding of wan_video_dit.py:131-137 (interleaved) or interactionv2.py:47-72 (rotate-half).
+ *   cos/sin: fp32 tables, row l for token l (see MOVA_ROPE_*), NULL when rope_mode == MOVA_ROPE_NONE
+ */
+int mova_b200_rmsnorm_rope(void* x, int64_t ldx, int L, int d, int head_dim, const void* w, float eps,
+                           const float* cos_tab, const float* sin_tab, int rope_mode, void* stream);
+
+/* out[i] = float(a[i]) + float(b[i]), bf16 inputs (b may be NULL): modulation + t_mod, wan_video_dit.py:279-280 */
+int mova_b200_add_to_f32(const void* a, const void* b, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVA_B200_H_ */
