@@ -1,8 +1,384 @@
-// placeholder until the tcgen05 attention kernel lands
+// Non-causal softmax attention forward on tcgen05, head_dim 128:  O = softmax(Q K^T * scale) V.
+//
+// Replaces flash_attention() (mova/diffusion/models/wan_video_dit.py:58-91) at its three call sites:
+// video / audio self-attention (:188), text cross-attention (:241) and the a2v / v2a bridge
+// (mova/diffusion/models/interactionv2.py:250).  q/k/v/o stay in the reference's flat [B, S, H*D] layout
+// (head h = columns [128h, 128h+128)), addressed through 3-D TMA tensor maps -- no rearrange copies.
+//
+// Design (B200), one CTA = 256 query rows (two 128-row tiles) x one head:
+//   * warps 0-3 / 4-7: softmax warpgroup of tile 0 / tile 1 (thread == one query row, TMEM lane == row),
+//     warp 8: TMA producer, warp 9: tcgen05 issuer + TMEM owner, warps 10-11 idle (register donors).
+//   * TMEM (512 columns): S0 | S1 | O0 | O1, fp32.  P (bf16) is written back over the first 64 columns of
+//     its S tile and consumed straight from TMEM as the A operand of the P.V MMA.
+//   * K and V tiles (128 keys x 128 dims, 32 KB) stream through one 5-slot ring in the order
+//     K0 V0 K1 V1 ...; V is used as an MN-major B operand, so no transpose is ever made.
+//   * the issuer interleaves  PV0(j) QK0(j+1) PV1(j) QK1(j+1)  so one tile's softmax overlaps the other
+//     tile's MMAs; tcgen05 executes in issue order, which is what makes the S/P aliasing safe.
+//   * online softmax in the exp2 domain with lazy rescaling: the running maximum baked into O and l is
+//     only advanced when the new block maximum exceeds it by more than 2^8, so O is touched rarely.
+//   * epilogue: O/l -> bf16 -> swizzled smem (the dead Q tile) -> TMA store (rows >= Sq are clipped).
+#include <stdlib.h>
+
+#include "common.cuh"
 #include "host_utils.h"
 #include "../../include/mova_b200.h"
-extern "C" int mova_b200_attn_fwd(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, int64_t,
-                                  int64_t, void*, int64_t, int64_t, float*, int, int, int, int, int, float, void*) {
-  mv::set_error("mova_b200_attn_fwd: not built yet");
-  return -1;
+
+namespace mv {
+
+constexpr int AT_THREADS = 384;
+constexpr int AT_NS = 5;  // K/V ring slots
+constexpr int AT_TILE_BYTES = 128 * 128 * 2;
+constexpr int AT_HALF_BYTES = AT_TILE_BYTES / 2;  // one 64-column (128-byte-wide) swizzle panel
+constexpr int AT_OFF_Q = 0;
+constexpr int AT_OFF_KV = 2 * AT_TILE_BYTES;
+constexpr int AT_OFF_BARS = AT_OFF_KV + AT_NS * AT_TILE_BYTES;
+constexpr int AT_BAR_QFULL = 0;                        // [2]
+constexpr int AT_BAR_KVFULL = 2;                       // [NS]
+constexpr int AT_BAR_KVEMPTY = AT_BAR_KVFULL + AT_NS;  // [NS]
+constexpr int AT_BAR_SFULL = AT_BAR_KVEMPTY + AT_NS;   // [2]
+constexpr int AT_BAR_PREADY = AT_BAR_SFULL + 2;        // [2]
+constexpr int AT_BAR_ODONE = AT_BAR_PREADY + 2;        // [2]
+constexpr int AT_NUM_BARS = AT_BAR_ODONE + 2;
+constexpr int AT_OFF_TMEM_PTR = AT_OFF_BARS + AT_NUM_BARS * 8;
+constexpr int AT_SMEM_BYTES = AT_OFF_TMEM_PTR + 16;
+static_assert(AT_SMEM_BYTES <= 232448, "attention shared memory budget exceeded");
+
+constexpr uint32_t AT_TMEM_S = 0;    // + 128 * tile
+constexpr uint32_t AT_TMEM_O = 256;  // + 128 * tile
+constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct AttnParams {
+  int Sq, Skv, H;
+  float scale;       // softmax scale
+  float scale_log2;  // scale * log2(e)
+  float* lse;        // [B, H, Sq] or null
+  uint32_t v_lbo, v_sbo;
+};
+
+__device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
+__device__ __forceinline__ void setmaxnreg_dec_88() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;"); }
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int row_base = blockIdx.x * 256;
+  const int nt = (row_base + 128 < p.Sq) ? 2 : 1;  // live query tiles of this CTA
+  const int n_kv = (p.Skv + 127) >> 7;
+
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars = smem_base + AT_OFF_BARS;
+  auto bar = [&](int idx) { return bars + 8u * idx; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + AT_OFF_TMEM_PTR);
+
+  if (threadIdx.x == 0) {
+    if ((smem_base & 1023u) != 0) __trap();  // swizzle-128B tiles need a 1024-byte aligned window
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) mbar_init(bar(AT_BAR_QFULL + i), 1);
+    for (int i = 0; i < AT_NS; ++i) {
+      mbar_init(bar(AT_BAR_KVFULL + i), 1);
+      mbar_init(bar(AT_BAR_KVEMPTY + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(AT_BAR_SFULL + i), 1);
+      mbar_init(bar(AT_BAR_PREADY + i), 4);  // one arrive per softmax warp
+      mbar_init(bar(AT_BAR_ODONE + i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 9) tmem_alloc<1>(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx < 8) {
+    // =========================== softmax warpgroups ===========================
+    setmaxnreg_inc_208();
+    const int tile = warp_idx >> 2;
+    if (tile < nt) {
+      const int r = (warp_idx & 3) * 32 + lane;  // row inside the tile == TMEM lane
+      const uint32_t lane_sel = static_cast<uint32_t>((warp_idx & 3) * 32) << 16;
+      const uint32_t t_s = tmem_base + lane_sel + AT_TMEM_S + tile * 128;
+      const uint32_t t_o = tmem_base + lane_sel + AT_TMEM_O + tile * 128;
+      const float c = p.scale_log2;
+      const int tail = p.Skv - (n_kv - 1) * 128;  // valid keys of the last block, 1..128
+      float m_used = -INFINITY;  // maximum (raw score units) the running O and l are expressed against
+      float l = 0.f;
+
+#pragma unroll 1
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(bar(AT_BAR_SFULL + tile), j & 1);
+        tc_fence_after();
+        uint32_t s[128];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld_x32(t_s + q * 32, reinterpret_cast<uint32_t(&)[32]>(s[q * 32]));
+        tmem_wait_ld();
+        if (j == n_kv - 1 && tail < 128) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= tail) s[i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+        if (j == 0) {
+          m_used = m_new;  // nothing accumulated yet
+        } else {
+          const bool need = (m_new - m_used) * c > AT_RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, need)) {
+            // PV(j-1) of this tile completed before S(j) was committed, so O is quiescent here
+            const float f = fast_exp2((m_used - m_new) * c);
+            m_used = m_new;
+            l *= f;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+              uint32_t o[32];
+              tmem_ld_x32(t_o + q * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_x32(t_o + q * 32, o);
+            }
+            tmem_wait_st();
+          }
+        }
+        const float neg = -m_used * c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(s[q * 32 + 2 * e]), c, neg));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(s[q * 32 + 2 * e + 1]), c, neg));
+            s[q * 32 + 2 * e] = __float_as_uint(p0);
+            s[q * 32 + 2 * e + 1] = __float_as_uint(p1);
+            pk[e] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_x16(t_s + q * 16, pk);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(AT_BAR_PREADY + tile));
+        // row sum, off the critical path
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          a0 += __uint_as_float(s[i]);
+          a1 += __uint_as_float(s[i + 1]);
+          a2 += __uint_as_float(s[i + 2]);
+          a3 += __uint_as_float(s[i + 3]);
+        }
+        l += (a0 + a1) + (a2 + a3);
+      }
+
+      // ---- epilogue: O / l -> bf16 -> swizzled smem (dead Q tile) -> TMA store ----
+      mbar_wait(bar(AT_BAR_ODONE + tile), 0);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const uint32_t stage = smem_base + AT_OFF_Q + tile * AT_TILE_BYTES;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o[32];
+        tmem_ld_x32(t_o + q * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            w[e] = pack_bf16x2(__uint_as_float(o[v * 8 + 2 * e]) * inv, __uint_as_float(o[v * 8 + 2 * e + 1]) * inv);
+          const int chunk16 = (q & 1) * 4 + v;
+          const uint32_t dst = stage + (q >> 1) * AT_HALF_BYTES + r * 128 + ((chunk16 ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                       "r"(w[3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + tile, 128);
+      const int row0 = row_base + tile * 128;
+      if ((threadIdx.x & 127) == 0) {
+        tma_store_3d(&tmO, stage, h * 128, row0, b);
+        tma_store_3d(&tmO, stage + AT_HALF_BYTES, h * 128 + 64, row0, b);
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
+      if (p.lse != nullptr && row0 + r < p.Sq)
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.Sq + row0 + r] = m_used * p.scale + __logf(l);
+    }
+  } else {
+    setmaxnreg_dec_88();
+    if (warp_idx == 8) {
+      // =========================== TMA producer ===========================
+      if (elect_one()) {
+        const int c0 = h * 128;
+        auto load_tile = [&](const CUtensorMap* m, uint32_t dst, uint32_t full, int row) {
+          mbar_arrive_expect_tx(full, AT_TILE_BYTES);
+          tma_load_3d(dst, m, full, c0, row, b);
+          tma_load_3d(dst + AT_HALF_BYTES, m, full, c0 + 64, row, b);
+        };
+        load_tile(&tmQ, smem_base + AT_OFF_Q, bar(AT_BAR_QFULL + 0), row_base);
+        uint32_t slot = 0, phase = 0;
+        for (int t = 0; t < 2 * n_kv; ++t) {
+          mbar_wait(bar(AT_BAR_KVEMPTY + slot), phase ^ 1);
+          load_tile((t & 1) ? &tmV : &tmK, smem_base + AT_OFF_KV + slot * AT_TILE_BYTES, bar(AT_BAR_KVFULL + slot),
+                    (t >> 1) * 128);
+          if (t == 0 && nt == 2)
+            load_tile(&tmQ, smem_base + AT_OFF_Q + AT_TILE_BYTES, bar(AT_BAR_QFULL + 1), row_base + 128);
+          if (++slot == AT_NS) { slot = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp_idx == 9) {
+      // =========================== tcgen05 issuer ===========================
+      if (elect_one()) {
+        constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 0, 1);
+        auto issue_qk = [&](int tile, uint32_t kbase) {
+          const uint32_t qb = smem_base + AT_OFF_Q + tile * AT_TILE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t off = (ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32;
+            umma_ss<1>(tmem_base + AT_TMEM_S + tile * 128, umma_desc_k_sw128(qb + off), umma_desc_k_sw128(kbase + off),
+                       IDESC_QK, ks > 0 ? 1u : 0u);
+          }
+        };
+        auto issue_pv = [&](int tile, uint32_t vbase, bool acc) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            umma_ts(tmem_base + AT_TMEM_O + tile * 128, tmem_base + AT_TMEM_S + tile * 128 + ks * 8,
+                    umma_desc_mn_sw128(vbase + ks * 2048, p.v_lbo, p.v_sbo), IDESC_PV, (acc || ks > 0) ? 1u : 0u);
+          }
+        };
+        uint32_t slot = 0, phase = 0;
+        auto next_slot = [&]() { if (++slot == AT_NS) { slot = 0; phase ^= 1; } };
+        auto slot_addr = [&](uint32_t s_) { return smem_base + AT_OFF_KV + s_ * AT_TILE_BYTES; };
+
+        // S(0) of both tiles
+        mbar_wait(bar(AT_BAR_QFULL + 0), 0);
+        mbar_wait(bar(AT_BAR_KVFULL + slot), phase);
+        tc_fence_after();
+        issue_qk(0, slot_addr(slot));
+        umma_commit(bar(AT_BAR_SFULL + 0));
+        if (nt == 2) {
+          mbar_wait(bar(AT_BAR_QFULL + 1), 0);
+          tc_fence_after();
+          issue_qk(1, slot_addr(slot));
+          umma_commit(bar(AT_BAR_SFULL + 1));
+        }
+        umma_commit(bar(AT_BAR_KVEMPTY + slot));
+        next_slot();
+
+        for (int j = 0; j < n_kv; ++j) {
+          const bool last = (j == n_kv - 1);
+          const uint32_t vslot = slot;
+          mbar_wait(bar(AT_BAR_KVFULL + vslot), phase);
+          next_slot();
+          const uint32_t kslot = slot;
+          mbar_wait(bar(AT_BAR_PREADY + 0), j & 1);
+          tc_fence_after();
+          issue_pv(0, slot_addr(vslot), j > 0);
+          if (last) umma_commit(bar(AT_BAR_ODONE + 0));
+          if (!last) {
+            mbar_wait(bar(AT_BAR_KVFULL + kslot), phase);
+            tc_fence_after();
+            issue_qk(0, slot_addr(kslot));
+            umma_commit(bar(AT_BAR_SFULL + 0));
+          }
+          if (nt == 2) {
+            mbar_wait(bar(AT_BAR_PREADY + 1), j & 1);
+            tc_fence_after();
+            issue_pv(1, slot_addr(vslot), j > 0);
+            if (last) umma_commit(bar(AT_BAR_ODONE + 1));
+          }
+          umma_commit(bar(AT_BAR_KVEMPTY + vslot));
+          if (!last) {
+            if (nt == 2) {
+              issue_qk(1, slot_addr(kslot));
+              umma_commit(bar(AT_BAR_SFULL + 1));
+            }
+            umma_commit(bar(AT_BAR_KVEMPTY + kslot));
+            next_slot();
+          }
+        }
+      }
+    }
+  }
+
+  // =========================== teardown ===========================
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
+}  // namespace mv
+
+extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs, int64_t k_ss,
+                                  const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs, int64_t o_ss,
+                                  float* lse, int B, int Sq, int Skv, int H, int D, float softmax_scale,
+                                  void* stream) {
+  using namespace mv;
+  MV_REQUIRE(q && k && v && o, "mova_b200_attn_fwd: null pointer");
+  MV_REQUIRE(D == 128, "mova_b200_attn_fwd: head_dim %d unsupported (the MOVA towers and bridge use 128)", D);
+  MV_REQUIRE(B >= 1 && H >= 1 && Sq >= 0 && Skv >= 1, "mova_b200_attn_fwd: bad shape B=%d Sq=%d Skv=%d H=%d", B, Sq,
+             Skv, H);
+  MV_REQUIRE(B <= 65535 && H <= 65535, "mova_b200_attn_fwd: B and H must fit a grid dimension");
+  MV_REQUIRE(softmax_scale > 0.f, "mova_b200_attn_fwd: softmax_scale must be positive");
+  const int64_t row = static_cast<int64_t>(H) * D;
+  MV_REQUIRE(q_ss >= row && k_ss >= row && v_ss >= row && o_ss >= row,
+             "mova_b200_attn_fwd: sequence stride smaller than H*D");
+  if (Sq == 0) return 0;
+  // a batch stride is irrelevant (and may be anything) when B == 1
+  if (B == 1) {
+    q_bs = q_ss * Sq;
+    o_bs = o_ss * Sq;
+    k_bs = k_ss * Skv;
+    v_bs = v_ss * Skv;
+  }
+
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = encode_tmap_3d(&tmQ, q, row, Sq, B, q_ss, q_bs, 64, 128, 1)) != 0) return rc;
+  if ((rc = encode_tmap_3d(&tmK, k, row, Skv, B, k_ss, k_bs, 64, 128, 1)) != 0) return rc;
+  if ((rc = encode_tmap_3d(&tmV, v, row, Skv, B, v_ss, v_bs, 64, 128, 1)) != 0) return rc;
+  if ((rc = encode_tmap_3d(&tmO, o, row, Sq, B, o_ss, o_bs, 64, 128, 1)) != 0) return rc;
+
+  AttnParams p;
+  p.Sq = Sq;
+  p.Skv = Skv;
+  p.H = H;
+  p.scale = softmax_scale;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.lse = lse;
+  p.v_lbo = AT_HALF_BYTES;  // distance between the two 64-wide head-dim panels of a V tile
+  p.v_sbo = 1024;           // distance between 8-key groups inside a panel
+
+  debug_attach();
+  static bool configured[64] = {false};
+  int dev = 0;
+  MV_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    MV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  dim3 grid((Sq + 255) / 256, H, B);
+  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
+  MV_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }

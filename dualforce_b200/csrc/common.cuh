@@ -93,10 +93,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #define MV_MBAR_TIMEOUT_CYCLES (6000000000LL)  // ~3-4 s of SM clock: a stuck pipeline traps, never hangs
 #endif
 
-static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
-  printf("[mova_b200] mbarrier wait timed out: block (%d,%d,%d) thread %d bar@%u parity %u\n",
-         blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+// Host-mapped (zero-copy) diagnostics record, one per translation unit (set by mv::debug_attach()).
+// A timed-out mbarrier wait writes {magic, bar, parity, block x/y/z, thread, kernel tag} there and traps;
+// the host can still read the record after the launch failure (mova_b200_debug_record()).
+// No printf / no call here on purpose: an ABI call inside the wait loop makes ptxas spill every live
+// register of the caller (seen as 2.6 KB of spills in the attention kernel).
+static __device__ uint32_t* g_mv_dbg = nullptr;
+
+__device__ __forceinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+  uint32_t* d = g_mv_dbg;
+  if (d != nullptr && atomicCAS(d, 0u, 0x4d564442u) == 0u) {
+    d[1] = bar;
+    d[2] = parity;
+    d[3] = blockIdx.x;
+    d[4] = blockIdx.y;
+    d[5] = blockIdx.z;
+    d[6] = threadIdx.x;
+    d[7] = 0u;
+    __threadfence_system();
+  }
   __trap();
+}
+
+// Host side: point this translation unit's g_mv_dbg at the library's pinned diagnostics record (once per device).
+int debug_device_pointer(uint32_t** dptr);  // host_utils.cu
+static inline int debug_attach() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!done[dev]) {
+    uint32_t* d = nullptr;
+    if (debug_device_pointer(&d) == 0 && d != nullptr) cudaMemcpyToSymbol(g_mv_dbg, &d, sizeof(d));
+    done[dev] = true;
+  }
+  return 0;
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {

@@ -92,10 +92,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::OFF_TMEM_PTR);
 
   if (threadIdx.x == 0) {
-    if ((smem_base & 1023u) != 0) {
-      printf("[mova_b200] gemm: dynamic smem base %u not 1024B aligned\n", smem_base);
-      __trap();
-    }
+    if ((smem_base & 1023u) != 0) __trap();  // swizzle-128B tiles need a 1024-byte aligned window
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
@@ -293,6 +290,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        cudaStream_t stream) {
   using Cfg = GemmCfg<CG>;
   auto kernel = gemm_bf16_kernel<CG, EPI>;
+  debug_attach();
   static bool configured[64] = {false};
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));

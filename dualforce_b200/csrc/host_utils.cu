@@ -28,6 +28,26 @@ int sm_count() {
   return cached[dev];
 }
 
+// Pinned, device-mapped diagnostics record (see common.cuh: mbar_timeout_trap).
+static uint32_t* g_dbg_host = nullptr;
+uint32_t* debug_host_record() {
+  if (g_dbg_host == nullptr) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    memset(p, 0, 64);
+    g_dbg_host = static_cast<uint32_t*>(p);
+  }
+  return g_dbg_host;
+}
+int debug_device_pointer(uint32_t** dptr) {
+  uint32_t* h = debug_host_record();
+  if (h == nullptr) return -1;
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return -1;
+  *dptr = static_cast<uint32_t*>(d);
+  return 0;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn == nullptr) {
@@ -102,6 +122,8 @@ extern "C" {
 int mova_b200_abi_version(void) { return MOVA_B200_ABI_VERSION; }
 
 const char* mova_b200_last_error(void) { return mv::get_error(); }
+
+const uint32_t* mova_b200_debug_record(void) { return mv::debug_host_record(); }
 
 int mova_b200_device_check(int device) {
   cudaDeviceProp prop;

@@ -31,6 +31,10 @@ const char* get_error();
     }                            \
   } while (0)
 
+// 16-word pinned record a trapping kernel fills in (word 0 == 0x4d564442 when valid)
+uint32_t* debug_host_record();
+int debug_device_pointer(uint32_t** dptr);
+
 // number of SMs of the current device (cached per device)
 int sm_count();
 

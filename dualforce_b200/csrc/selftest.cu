@@ -18,11 +18,18 @@
 
 #include "../../include/mova_b200.h"
 
+static void dump_debug_record() {
+  const uint32_t* d = mova_b200_debug_record();
+  if (d != nullptr && d[0] == 0x4d564442u)
+    printf("  pipeline time-out record: mbarrier smem 0x%x parity %u block (%u,%u,%u) thread %u\n", d[1], d[2], d[3],
+           d[4], d[5], d[6]);
+}
 #define CK(x)                                                                                   \
   do {                                                                                          \
     cudaError_t e_ = (x);                                                                       \
     if (e_ != cudaSuccess) {                                                                    \
       printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_));   \
+      dump_debug_record();                                                                      \
       exit(3);                                                                                  \
     }                                                                                           \
   } while (0)

@@ -39,6 +39,12 @@ extern "C" {
 int mova_b200_abi_version(void);
 const char* mova_b200_last_error(void);
 
+/*
+ * Diagnostics: 16 host-visible words a kernel fills in before trapping on a pipeline time-out
+ * {0x4d564442, mbarrier smem address, parity, blockIdx.x/y/z, threadIdx.x, 0...}; word 0 is 0 when nothing tripped.
+ */
+const uint32_t* mova_b200_debug_record(void);
+
 /* 0 if `device` is an sm_100 part the kernels can run on, negative otherwise. */
 int mova_b200_device_check(int device);
 
