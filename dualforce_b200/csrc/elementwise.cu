@@ -126,12 +126,18 @@ constexpr int RR_MAXP = 4;  // vector pairs per thread -> d up to 128 * 4 * 16 =
 
 template <int ROPE>
 __global__ void __launch_bounds__(EW_THREADS)
-rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int d, const __nv_bfloat16* __restrict__ w,
-                    float eps, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab) {
+rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int d, int seg_vecs, long long seg_stride,
+                    const __nv_bfloat16* __restrict__ w, float eps, const float* __restrict__ cos_tab,
+                    const float* __restrict__ sin_tab) {
   __shared__ float red[4];
   const long long row = blockIdx.x;
   const int npair = d >> 4;
-  uint4* xr = reinterpret_cast<uint4*>(x + row * ldx);
+  // logical 16-byte vector v of the row lives in segment v / seg_vecs (segments are seg_stride elements apart)
+  __nv_bfloat16* xrow = x + row * ldx;
+  auto vec_ptr = [&](int v) -> uint4* {
+    const int seg = v / seg_vecs;
+    return reinterpret_cast<uint4*>(xrow + seg * seg_stride) + (v - seg * seg_vecs);
+  };
   uint4 lo[RR_MAXP], hi[RR_MAXP];
   float ss = 0.f;
 #pragma unroll
@@ -139,8 +145,8 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int d, const _
     const int pi = threadIdx.x + i * EW_THREADS;
     if (pi < npair) {
       const int v = (pi >> 3) * 16 + (pi & 7);
-      lo[i] = xr[v];
-      hi[i] = xr[v + 8];
+      lo[i] = *vec_ptr(v);
+      hi[i] = *vec_ptr(v + 8);
     }
   }
 #pragma unroll
@@ -209,8 +215,8 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int d, const _
           b[e] = x2 * c2[e] + x1 * s2[e];
         }
       }
-      xr[v] = pack8(a);
-      xr[v + 8] = pack8(b);
+      *vec_ptr(v) = pack8(a);
+      *vec_ptr(v + 8) = pack8(b);
     }
   }
 }
@@ -281,10 +287,19 @@ int mova_b200_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int L,
 
 int mova_b200_rmsnorm_rope(void* x, int64_t ldx, int L, int d, int head_dim, const void* w, float eps,
                            const float* cos_tab, const float* sin_tab, int rope_mode, void* stream) {
+  return mova_b200_rmsnorm_rope_seg(x, ldx, d, 0, L, d, head_dim, w, eps, cos_tab, sin_tab, rope_mode, stream);
+}
+
+int mova_b200_rmsnorm_rope_seg(void* x, int64_t ldx, int seg_len, int64_t seg_stride, int L, int d, int head_dim,
+                               const void* w, float eps, const float* cos_tab, const float* sin_tab, int rope_mode,
+                               void* stream) {
   using namespace mv;
   MV_REQUIRE(x && w, "mova_b200_rmsnorm_rope: null pointer");
   MV_REQUIRE(d > 0 && d % 128 == 0 && d <= EW_THREADS * RR_MAXP * 16, "mova_b200_rmsnorm_rope: d=%d unsupported", d);
-  MV_REQUIRE(ldx % 8 == 0 && ldx >= d, "mova_b200_rmsnorm_rope: bad leading dimension");
+  MV_REQUIRE(seg_len > 0 && seg_len % 128 == 0 && d % seg_len == 0,
+             "mova_b200_rmsnorm_rope: seg_len (%d) must be a multiple of 128 dividing d (%d)", seg_len, d);
+  MV_REQUIRE(ldx % 8 == 0 && ldx >= seg_len && seg_stride % 8 == 0, "mova_b200_rmsnorm_rope: bad leading dimension");
+  const int seg_vecs = seg_len / 8;
   MV_REQUIRE(rope_mode >= MOVA_ROPE_NONE && rope_mode <= MOVA_ROPE_HALF, "mova_b200_rmsnorm_rope: bad rope_mode %d",
              rope_mode);
   if (rope_mode != MOVA_ROPE_NONE) {
@@ -296,11 +311,11 @@ int mova_b200_rmsnorm_rope(void* x, int64_t ldx, int L, int d, int head_dim, con
   auto* xp = static_cast<__nv_bfloat16*>(x);
   const auto* wp = static_cast<const __nv_bfloat16*>(w);
   if (rope_mode == MOVA_ROPE_NONE)
-    rmsnorm_rope_kernel<MOVA_ROPE_NONE><<<L, EW_THREADS, 0, s>>>(xp, ldx, d, wp, eps, cos_tab, sin_tab);
+    rmsnorm_rope_kernel<MOVA_ROPE_NONE><<<L, EW_THREADS, 0, s>>>(xp, ldx, d, seg_vecs, seg_stride, wp, eps, cos_tab, sin_tab);
   else if (rope_mode == MOVA_ROPE_INTERLEAVED)
-    rmsnorm_rope_kernel<MOVA_ROPE_INTERLEAVED><<<L, EW_THREADS, 0, s>>>(xp, ldx, d, wp, eps, cos_tab, sin_tab);
+    rmsnorm_rope_kernel<MOVA_ROPE_INTERLEAVED><<<L, EW_THREADS, 0, s>>>(xp, ldx, d, seg_vecs, seg_stride, wp, eps, cos_tab, sin_tab);
   else
-    rmsnorm_rope_kernel<MOVA_ROPE_HALF><<<L, EW_THREADS, 0, s>>>(xp, ldx, d, wp, eps, cos_tab, sin_tab);
+    rmsnorm_rope_kernel<MOVA_ROPE_HALF><<<L, EW_THREADS, 0, s>>>(xp, ldx, d, seg_vecs, seg_stride, wp, eps, cos_tab, sin_tab);
   MV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

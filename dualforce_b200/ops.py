@@ -1,0 +1,239 @@
+"""Torch-tensor front end of the C ABI: each function validates layouts, passes raw device pointers and the
+current CUDA stream to ``libmova_b200.so`` and returns torch tensors.  No arithmetic happens in Python and there
+is no fallback: a CPU tensor, a wrong dtype or a missing library raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_GELU_TANH, EPI_RESIDUAL, ROPE_HALF, ROPE_INTERLEAVED, ROPE_NONE  # noqa: F401
+
+__all__ = [
+    "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32",
+    "EPI_BIAS", "EPI_GELU_TANH", "EPI_RESIDUAL", "ROPE_NONE", "ROPE_INTERLEAVED", "ROPE_HALF",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.MovaB200Error(f"{name} must be a CUDA tensor (dualforce_b200 has no CPU path); got {t.device}")
+    if t.dtype != dtype:
+        raise _lib.MovaB200Error(f"{name} must be {dtype}, got {t.dtype}")
+    _lib.require_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _rows2d(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
+    """(rows, cols, leading dimension) of a tensor viewed as a row-major matrix whose last dim is contiguous."""
+    if t.dim() < 2:
+        raise _lib.MovaB200Error(f"{name}: need at least 2 dims, got shape {tuple(t.shape)}")
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise _lib.MovaB200Error(f"{name}: last dimension must be contiguous (strides {t.stride()})")
+    cols = t.shape[-1]
+    rows = t.numel() // cols if cols else 0
+    ld = t.stride(-2)
+    # leading dims must collapse onto one row stride
+    expect = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != expect:
+            raise _lib.MovaB200Error(f"{name}: shape {tuple(t.shape)} strides {t.stride()} is not a strided matrix")
+        expect *= t.shape[d]
+    return rows, cols, ld
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS,
+           residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, scale: float = 1.0,
+           out: Optional[torch.Tensor] = None, cta_group: int = 0, segments: int = 1) -> torch.Tensor:
+    """``epi(x @ weight.T + bias)`` -- nn.Linear (wan_video_dit.py:171-174) with the GELU-tanh (:270-271) or
+    gated-residual (:254-255, interactionv2.py:535) step fused into the tcgen05 GEMM epilogue.
+
+    x: [..., K] bf16 (row stride arbitrary), weight: [N, K] bf16, bias: [N] bf16, gate: [N] fp32,
+    residual: [..., N] bf16 (may be ``out``).  Returns [..., N] bf16.
+
+    ``segments > 1``: x is ``[segments, M, K/segments]`` (contiguous) and is read as the matrix
+    ``A[m, s*K/segments + c] = x[s, m, c]`` -- the layout the context-parallel all-to-all delivers.
+    """
+    _need(x, torch.bfloat16, "x")
+    _need(weight, torch.bfloat16, "weight")
+    if segments > 1:
+        if x.dim() != 3 or x.shape[0] != segments or not x.is_contiguous():
+            raise _lib.MovaB200Error(f"linear: segmented x must be contiguous [segments, M, seg_k], got {tuple(x.shape)}")
+        M, seg_k = x.shape[1], x.shape[2]
+        K, lda, seg_stride = seg_k * segments, seg_k, M * seg_k
+        out_shape = (M,)
+    else:
+        M, K, lda = _rows2d(x, "x")
+        seg_k, seg_stride = K, 0
+        out_shape = tuple(x.shape[:-1])
+    N, Kw, ldw = _rows2d(weight, "weight")
+    if Kw != K:
+        raise _lib.MovaB200Error(f"linear: x has K={K}, weight has K={Kw}")
+    if out is None:
+        out = torch.empty(*out_shape, N, dtype=torch.bfloat16, device=x.device)
+    else:
+        _need(out, torch.bfloat16, "out")
+    Mo, No, ldc = _rows2d(out, "out")
+    if (Mo, No) != (M, N):
+        raise _lib.MovaB200Error(f"linear: out is {Mo}x{No}, expected {M}x{N}")
+    res_ptr, ldr = None, 0
+    if epilogue == EPI_RESIDUAL:
+        if residual is None:
+            raise _lib.MovaB200Error("linear: EPI_RESIDUAL needs `residual`")
+        _need(residual, torch.bfloat16, "residual")
+        Mr, Nr, ldr = _rows2d(residual, "residual")
+        if (Mr, Nr) != (M, N):
+            raise _lib.MovaB200Error(f"linear: residual is {Mr}x{Nr}, expected {M}x{N}")
+        res_ptr = residual.data_ptr()
+    gate_ptr = None
+    if gate is not None:
+        _need(gate, torch.float32, "gate")
+        if gate.numel() != N or not gate.is_contiguous():
+            raise _lib.MovaB200Error("linear: gate must be a contiguous fp32 vector of N elements")
+        gate_ptr = gate.data_ptr()
+    bias_ptr = None
+    if bias is not None:
+        _need(bias, torch.bfloat16, "bias")
+        if bias.numel() != N or not bias.is_contiguous():
+            raise _lib.MovaB200Error("linear: bias must be a contiguous bf16 vector of N elements")
+        bias_ptr = bias.data_ptr()
+    rc = _lib.load().mova_b200_linear_segk(x.data_ptr(), lda, seg_k, seg_stride, weight.data_ptr(), ldw, bias_ptr,
+                                           out.data_ptr(), ldc, M, N, K, epilogue, res_ptr, ldr, gate_ptr, float(scale),
+                                           cta_group, _stream())
+    _lib.check(rc, "mova_b200_linear")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, *, return_lse: bool = False,
+              softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None):
+    """``softmax(q k^T / sqrt(D)) v`` on the flat ``[B, S, H*D]`` layout of flash_attention()
+    (wan_video_dit.py:58-91).  q/k/v may be column slices of a fused projection buffer (any row stride).
+
+    Returns ``[B, Sq, H*D]`` bf16 (and ``lse [B, H, Sq]`` fp32, natural log, when ``return_lse``).
+    """
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, torch.bfloat16, n)
+        if t.dim() != 3 or t.stride(2) != 1:
+            raise _lib.MovaB200Error(f"attention: {n} must be [B, S, H*D] with a contiguous last dim")
+    B, Sq, HD = q.shape
+    Skv = k.shape[1]
+    if HD % num_heads:
+        raise _lib.MovaB200Error(f"attention: channel dim {HD} not divisible by num_heads {num_heads}")
+    D = HD // num_heads
+    if k.shape != (B, Skv, HD) or v.shape != (B, Skv, HD):
+        raise _lib.MovaB200Error(f"attention: k/v shapes {tuple(k.shape)}/{tuple(v.shape)} do not match q {tuple(q.shape)}")
+    if out is None:
+        out = torch.empty(B, Sq, HD, dtype=torch.bfloat16, device=q.device)
+    else:
+        _need(out, torch.bfloat16, "out")
+        if out.shape != (B, Sq, HD) or out.stride(2) != 1:
+            raise _lib.MovaB200Error("attention: bad `out`")
+    lse = torch.empty(B, num_heads, Sq, dtype=torch.float32, device=q.device) if return_lse else None
+    scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(D)
+    rc = _lib.load().mova_b200_attn_fwd(
+        q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
+        v.stride(1), out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr() if lse is not None else None, B, Sq,
+        Skv, num_heads, D, float(scale), _stream())
+    _lib.check(rc, "mova_b200_attn_fwd")
+    return (out, lse) if return_lse else out
+
+
+def layernorm(x: torch.Tensor, eps: float, *, weight: Optional[torch.Tensor] = None,
+              bias: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+              scale: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One-pass ``LayerNorm(x) [*weight + bias] [*(1 + scale) + shift]``: nn.LayerNorm + modulate()
+    (wan_video_dit.py:94-96, 267-269, 286, 289; interactionv2.py:322, 349).  shift/scale: fp32 [d]."""
+    _need(x, torch.bfloat16, "x")
+    L, d, ldx = _rows2d(x, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _need(out, torch.bfloat16, "out")
+    Lo, do, ldy = _rows2d(out, "out")
+    if (Lo, do) != (L, d):
+        raise _lib.MovaB200Error("layernorm: out shape mismatch")
+    ptr = {}
+    for name, t, dt in (("weight", weight, torch.bfloat16), ("bias", bias, torch.bfloat16),
+                        ("shift", shift, torch.float32), ("scale", scale, torch.float32)):
+        if t is None:
+            ptr[name] = None
+        else:
+            _need(t, dt, name)
+            if t.numel() != d or not t.is_contiguous():
+                raise _lib.MovaB200Error(f"layernorm: {name} must be a contiguous vector of {d} elements")
+            ptr[name] = t.data_ptr()
+    rc = _lib.load().mova_b200_layernorm(x.data_ptr(), ldx, out.data_ptr(), ldy, L, d, float(eps), ptr["weight"],
+                                         ptr["bias"], ptr["shift"], ptr["scale"], _stream())
+    _lib.check(rc, "mova_b200_layernorm")
+    return out
+
+
+def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, eps: float, *, head_dim: int = 128,
+                  cos: Optional[torch.Tensor] = None, sin: Optional[torch.Tensor] = None,
+                  rope_mode: int = ROPE_NONE, segments: int = 1, seg_stride: int = 0) -> torch.Tensor:
+    """In place ``x = RoPE(RMSNorm_d(x) * weight)`` with the RMS taken over all ``d = H*head_dim`` channels
+    (torch.nn.RMSNorm(dim), wan_video_dit.py:175-176) and RoPE in the interleaved (wan_video_dit.py:131-137) or
+    rotate-half (interactionv2.py:47-72) convention.  cos/sin: fp32 ``[L, 64]`` / ``[L, 128]`` tables.
+
+    ``segments > 1``: ``x`` is the ``[L, d/segments]`` view of segment 0 and segment s starts ``s * seg_stride``
+    elements later (the destination-rank-major q/k/v buffer of the context-parallel path)."""
+    _need(x, torch.bfloat16, "x")
+    _need(weight, torch.bfloat16, "weight")
+    L, seg_len, ldx = _rows2d(x, "x")
+    d = seg_len * segments
+    if weight.numel() != d or not weight.is_contiguous():
+        raise _lib.MovaB200Error("rmsnorm_rope_: weight must be a contiguous bf16 vector of d elements")
+    cptr = sptr = None
+    if rope_mode != ROPE_NONE:
+        width = head_dim // 2 if rope_mode == ROPE_INTERLEAVED else head_dim
+        for t, n in ((cos, "cos"), (sin, "sin")):
+            if t is None:
+                raise _lib.MovaB200Error("rmsnorm_rope_: RoPE tables missing")
+            _need(t, torch.float32, n)
+            if not t.is_contiguous() or t.numel() != L * width:
+                raise _lib.MovaB200Error(f"rmsnorm_rope_: {n} must be contiguous fp32 [{L}, {width}], got {tuple(t.shape)}")
+        cptr, sptr = cos.data_ptr(), sin.data_ptr()
+    rc = _lib.load().mova_b200_rmsnorm_rope_seg(x.data_ptr(), ldx, seg_len, int(seg_stride), L, d, head_dim,
+                                                weight.data_ptr(), float(eps), cptr, sptr, rope_mode, _stream())
+    _lib.check(rc, "mova_b200_rmsnorm_rope")
+    return x
+
+
+def lse_merge(o_parts: torch.Tensor, lse_parts: torch.Tensor, num_heads: int, *, return_lse: bool = False):
+    """Combine partial attention results over disjoint key sets: ``o_parts [P, rows, H*D]`` bf16 and
+    ``lse_parts [P, H, rows]`` fp32 -> ``[rows, H*D]`` (split-KV and the context-parallel v2a bridge)."""
+    _need(o_parts, torch.bfloat16, "o_parts")
+    _need(lse_parts, torch.float32, "lse_parts")
+    if not o_parts.is_contiguous() or not lse_parts.is_contiguous() or o_parts.dim() != 3 or lse_parts.dim() != 3:
+        raise _lib.MovaB200Error("lse_merge: o_parts [P, rows, H*D] and lse_parts [P, H, rows] must be contiguous")
+    P, rows, HD = o_parts.shape
+    if lse_parts.shape != (P, num_heads, rows):
+        raise _lib.MovaB200Error(f"lse_merge: lse_parts shape {tuple(lse_parts.shape)} != {(P, num_heads, rows)}")
+    out = torch.empty(rows, HD, dtype=torch.bfloat16, device=o_parts.device)
+    lse = torch.empty(num_heads, rows, dtype=torch.float32, device=o_parts.device) if return_lse else None
+    rc = _lib.load().mova_b200_lse_merge(o_parts.data_ptr(), lse_parts.data_ptr(), P, out.data_ptr(), HD,
+                                         lse.data_ptr() if lse is not None else None, rows, num_heads,
+                                         HD // num_heads, _stream())
+    _lib.check(rc, "mova_b200_lse_merge")
+    return (out, lse) if return_lse else out
+
+
+def add_to_f32(a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``float(a) + float(b)`` for bf16 inputs: ``modulation + t_mod`` of DiTBlock (wan_video_dit.py:279-280),
+    kept in fp32 so shift/scale/gate enter the fused kernels unrounded."""
+    _need(a, torch.bfloat16, "a")
+    a = a.contiguous()
+    bptr = None
+    if b is not None:
+        _need(b, torch.bfloat16, "b")
+        b = b.expand_as(a).contiguous()
+        bptr = b.data_ptr()
+    out = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+    rc = _lib.load().mova_b200_add_to_f32(a.data_ptr(), bptr, out.data_ptr(), a.numel(), _stream())
+    _lib.check(rc, "mova_b200_add_to_f32")
+    return out

@@ -63,6 +63,18 @@ int mova_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, con
                      const float* gate, float scale, int cta_group, void* stream);
 
 /*
+ * Same, with the A operand split along K into K/seg_k segments that live `seg_stride` elements apart:
+ *   A(m, k) = A[(k / seg_k) * seg_stride + m * lda + (k % seg_k)],   seg_k % 64 == 0.
+ * This is the layout an all-to-all leaves the attention output in under context parallelism
+ * ([source rank][token][heads of that rank]); the o-projection reads it in place (mova/distributed, yunchang
+ * LongContextAttention called from wan_video_dit.py:207 does a separate inverse all-to-all + permute instead).
+ */
+int mova_b200_linear_segk(const void* A, int64_t lda, int seg_k, int64_t seg_stride, const void* W, int64_t ldw,
+                          const void* bias, void* C, int64_t ldc, int M, int N, int K, int epilogue,
+                          const void* residual, int64_t ldr, const float* gate, float scale, int cta_group,
+                          void* stream);
+
+/*
  * Non-causal softmax attention, head_dim 128: O = softmax(Q K^T * softmax_scale) V.
  * Replaces flash_attention() at wan_video_dit.py:58-91 (called from :188, :241, interactionv2.py:250).
  *   q: [B, Sq, H, 128]  element (b,s,h,d) at q + b*q_bs + s*q_ss + h*128 + d   (same for k, v, o)
@@ -98,6 +110,15 @@ int mova_b200_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int L,
  */
 int mova_b200_rmsnorm_rope(void* x, int64_t ldx, int L, int d, int head_dim, const void* w, float eps,
                            const float* cos_tab, const float* sin_tab, int rope_mode, void* stream);
+
+/*
+ * Same, for a row stored as d/seg_len segments of seg_len channels (a multiple of 128) that live `seg_stride`
+ * elements apart: channel c of token l is x[(c / seg_len) * seg_stride + l * ldx + (c % seg_len)].  Used on the
+ * destination-rank-major q/k/v buffer of the context-parallel path, before its all-to-all.
+ */
+int mova_b200_rmsnorm_rope_seg(void* x, int64_t ldx, int seg_len, int64_t seg_stride, int L, int d, int head_dim,
+                               const void* w, float eps, const float* cos_tab, const float* sin_tab, int rope_mode,
+                               void* stream);
 
 /* out[i] = float(a[i]) + float(b[i]), bf16 inputs (b may be NULL): modulation + t_mod, wan_video_dit.py:279-280 */
 int mova_b200_add_to_f32(const void* a, const void* b, float* out, int64_t n, void* stream);
