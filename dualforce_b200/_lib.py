@@ -25,10 +25,10 @@ SIGNATURES = {
         [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
          c_int64, c_void_p, c_float, c_int, c_void_p],
     ),
-    "mova_b200_linear_segk": (
+    "mova_b200_linear_ex": (
         c_int,
-        [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
-         c_void_p, c_int64, c_void_p, c_float, c_int, c_void_p],
+        [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_int,
+         c_int, c_int, c_void_p, c_int64, c_void_p, c_float, c_int, c_void_p],
     ),
     "mova_b200_attn_fwd": (
         c_int,
@@ -90,7 +90,13 @@ def last_error() -> str:
     return msg.decode("utf-8", "replace") if msg else ""
 
 
+LAUNCHES = 0  # kernel launches issued through the C ABI (each entry point enqueues exactly one kernel)
+_TIMERS = None  # bench.py sets this to a list; ops.attention then appends (start_event, end_event, B, Sq, Skv, H, D)
+
+
 def check(rc: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         raise MovaB200Error(f"{what} failed (code {rc}): {last_error()}")
 
@@ -99,5 +105,7 @@ def require_device(index: int) -> None:
     """Raise unless CUDA device ``index`` can run the sm_100a kernels."""
     if index in _checked_devices:
         return
-    check(load().mova_b200_device_check(int(index)), f"mova_b200_device_check({index})")
+    rc = load().mova_b200_device_check(int(index))
+    if rc != 0:
+        raise MovaB200Error(f"mova_b200_device_check({index}) failed (code {rc}): {last_error()}")
     _checked_devices.add(index)

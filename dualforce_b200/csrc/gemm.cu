@@ -45,7 +45,8 @@ struct GemmCfg {
 
 struct GemmParams {
   int M, N, K;
-  int seg_k;  // A is split along K into segments of seg_k columns living seg_stride apart (3rd TMA dimension)
+  int seg_k;  // A is split along K into segments of seg_k columns living a_seg_stride apart (3rd TMA dimension)
+  int seg_n;  // C is split along N into segments of seg_n columns living c_seg_stride apart (3rd TMA dimension)
   const __nv_bfloat16* bias;      // [N] or null
   const __nv_bfloat16* residual;  // [M, ldr] or null
   long long ldr;
@@ -267,7 +268,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (et == 0) {
-          tma_store_2d(&tmC, buf, ncol0, row0);
+          const int cseg = ncol0 / p.seg_n;
+          tma_store_3d(&tmC, buf, ncol0 - cseg * p.seg_n, row0, cseg);
           tma_store_commit();
         }
       }
@@ -328,21 +330,27 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 extern "C" int mova_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C,
                                 int64_t ldc, int M, int N, int K, int epilogue, const void* residual, int64_t ldr,
                                 const float* gate, float scale, int cta_group, void* stream) {
-  return mova_b200_linear_segk(A, lda, K, 0, W, ldw, bias, C, ldc, M, N, K, epilogue, residual, ldr, gate, scale,
-                               cta_group, stream);
+  return mova_b200_linear_ex(A, lda, K, 0, W, ldw, bias, C, ldc, N, 0, M, N, K, epilogue, residual, ldr, gate, scale,
+                             cta_group, stream);
 }
 
-extern "C" int mova_b200_linear_segk(const void* A, int64_t lda, int seg_k, int64_t seg_stride, const void* W,
-                                     int64_t ldw, const void* bias, void* C, int64_t ldc, int M, int N, int K,
-                                     int epilogue, const void* residual, int64_t ldr, const float* gate, float scale,
-                                     int cta_group, void* stream) {
+extern "C" int mova_b200_linear_ex(const void* A, int64_t lda, int seg_k, int64_t seg_stride, const void* W,
+                                   int64_t ldw, const void* bias, void* C, int64_t ldc, int seg_n,
+                                   int64_t c_seg_stride, int M, int N, int K, int epilogue, const void* residual,
+                                   int64_t ldr, const float* gate, float scale, int cta_group, void* stream) {
   using namespace mv;
   MV_REQUIRE(A && W && C, "mova_b200_linear: null operand pointer");
   MV_REQUIRE(M >= 0 && N > 0 && K > 0, "mova_b200_linear: bad shape M=%d N=%d K=%d", M, N, K);
   MV_REQUIRE(N % 8 == 0 && K % 8 == 0, "mova_b200_linear: N (%d) and K (%d) must be multiples of 8", N, K);
   MV_REQUIRE(seg_k > 0 && seg_k <= K && K % seg_k == 0, "mova_b200_linear: seg_k (%d) must divide K (%d)", seg_k, K);
   MV_REQUIRE(seg_k == K || seg_k % GEMM_BK == 0, "mova_b200_linear: a segmented A needs seg_k %% %d == 0", GEMM_BK);
-  MV_REQUIRE(lda >= seg_k && ldw >= K && ldc >= N, "mova_b200_linear: leading dimension smaller than row length");
+  MV_REQUIRE(seg_n > 0 && seg_n <= N && N % seg_n == 0, "mova_b200_linear: seg_n (%d) must divide N (%d)", seg_n, N);
+  MV_REQUIRE(seg_n == N || seg_n % 64 == 0, "mova_b200_linear: a segmented C needs seg_n %% 64 == 0");
+  MV_REQUIRE(seg_n == N || epilogue != MOVA_EPI_RESIDUAL, "mova_b200_linear: residual epilogue with a segmented C");
+  MV_REQUIRE(lda >= seg_k && ldw >= K && ldc >= seg_n, "mova_b200_linear: leading dimension smaller than row length");
+  const int ncseg = N / seg_n;
+  if (ncseg == 1) c_seg_stride = ldc * static_cast<int64_t>(M > 0 ? M : 1);
+  MV_REQUIRE(c_seg_stride % 8 == 0 && c_seg_stride > 0, "mova_b200_linear: c_seg_stride must be a positive multiple of 8");
   const int nseg = K / seg_k;
   if (nseg == 1) seg_stride = lda * static_cast<int64_t>(M > 0 ? M : 1);
   MV_REQUIRE(seg_stride % 8 == 0 && seg_stride > 0, "mova_b200_linear: seg_stride must be a positive multiple of 8");
@@ -360,11 +368,12 @@ extern "C" int mova_b200_linear_segk(const void* A, int64_t lda, int seg_k, int6
   int rc;
   if ((rc = encode_tmap_3d(&tmA, A, seg_k, M, nseg, lda, seg_stride, GEMM_BK, GEMM_BM, 1)) != 0) return rc;
   if ((rc = encode_tmap_2d(&tmB, W, K, N, ldw, GEMM_BK, GEMM_BN / cta_group)) != 0) return rc;
-  if ((rc = encode_tmap_2d(&tmC, C, N, M, ldc, 64, GEMM_BM)) != 0) return rc;
+  if ((rc = encode_tmap_3d(&tmC, C, seg_n, M, ncseg, ldc, c_seg_stride, 64, GEMM_BM, 1)) != 0) return rc;
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.seg_k = seg_k;
+  p.seg_n = seg_n;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.ldr = ldr;

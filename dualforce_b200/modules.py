@@ -254,7 +254,13 @@ class RotaryEmbedding(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, position_ids):
-        inv = self.inv_freq[None, :, None].float().expand(position_ids.shape[0], -1, 1).to(x.device)
+        # Recomputed in fp32 on every (memoised) call instead of read from the buffer: ``module.to(torch.bfloat16)``
+        # -- how the reference loads its bf16 checkpoint -- also rounds the ``inv_freq`` buffer to bf16, which
+        # perturbs every RoPE frequency by up to 2^-9 (0.8 rad at audio position 400).  The fp32 oracle, and a model
+        # trained with fp32 buffers, use the exact frequencies; so does this path (deviations).
+        inv_freq = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.int64).to(
+            device=x.device, dtype=torch.float) / self.dim))
+        inv = inv_freq[None, :, None].float().expand(position_ids.shape[0], -1, 1)
         pos = position_ids[:, None, :].float()
         freqs = (inv.float() @ pos.float()).transpose(1, 2)
         emb = torch.cat((freqs, freqs), dim=-1)
@@ -439,7 +445,7 @@ class DualTowerConditionalBridge(nn.Module):
         if br.head_dim != 128:
             raise NotImplementedError("the sm_100a attention kernel is built for head_dim 128 (MOVA's value)")
         br.condition_scale = ref.condition_scale
-        br.rotary = ref.rotary
+        br.rotary = RotaryEmbedding(base=10000.0, dim=br.head_dim)  # fp32-stable twin, see RotaryEmbedding.forward
         br.audio_to_video_conditioners = nn.ModuleDict(
             {k: ConditionalCrossAttentionBlock.from_reference(m) for k, m in ref.audio_to_video_conditioners.items()})
         br.video_to_audio_conditioners = nn.ModuleDict(

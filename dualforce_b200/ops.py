@@ -50,7 +50,8 @@ def _rows2d(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS,
            residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, scale: float = 1.0,
-           out: Optional[torch.Tensor] = None, cta_group: int = 0, segments: int = 1) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, cta_group: int = 0, segments: int = 1,
+           out_segments: int = 1) -> torch.Tensor:
     """``epi(x @ weight.T + bias)`` -- nn.Linear (wan_video_dit.py:171-174) with the GELU-tanh (:270-271) or
     gated-residual (:254-255, interactionv2.py:535) step fused into the tcgen05 GEMM epilogue.
 
@@ -59,6 +60,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 
     ``segments > 1``: x is ``[segments, M, K/segments]`` (contiguous) and is read as the matrix
     ``A[m, s*K/segments + c] = x[s, m, c]`` -- the layout the context-parallel all-to-all delivers.
+    ``out_segments > 1``: the result is written as ``out[s, m, c] = C[m, s*N/out_segments + c]`` into a contiguous
+    ``[out_segments, M, N/out_segments]`` buffer -- the layout the context-parallel all-to-all sends.
     """
     _need(x, torch.bfloat16, "x")
     _need(weight, torch.bfloat16, "weight")
@@ -75,13 +78,25 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     N, Kw, ldw = _rows2d(weight, "weight")
     if Kw != K:
         raise _lib.MovaB200Error(f"linear: x has K={K}, weight has K={Kw}")
-    if out is None:
-        out = torch.empty(*out_shape, N, dtype=torch.bfloat16, device=x.device)
-    else:
+    if out_segments > 1:
+        if N % out_segments:
+            raise _lib.MovaB200Error(f"linear: N={N} not divisible by out_segments={out_segments}")
+        seg_n = N // out_segments
+        if out is None:
+            out = torch.empty(out_segments, M, seg_n, dtype=torch.bfloat16, device=x.device)
         _need(out, torch.bfloat16, "out")
-    Mo, No, ldc = _rows2d(out, "out")
-    if (Mo, No) != (M, N):
-        raise _lib.MovaB200Error(f"linear: out is {Mo}x{No}, expected {M}x{N}")
+        if tuple(out.shape) != (out_segments, M, seg_n) or not out.is_contiguous():
+            raise _lib.MovaB200Error(f"linear: segmented out must be contiguous {(out_segments, M, seg_n)}")
+        ldc, c_seg_stride = seg_n, M * seg_n
+    else:
+        seg_n, c_seg_stride = N, 0
+        if out is None:
+            out = torch.empty(*out_shape, N, dtype=torch.bfloat16, device=x.device)
+        else:
+            _need(out, torch.bfloat16, "out")
+        Mo, No, ldc = _rows2d(out, "out")
+        if (Mo, No) != (M, N):
+            raise _lib.MovaB200Error(f"linear: out is {Mo}x{No}, expected {M}x{N}")
     res_ptr, ldr = None, 0
     if epilogue == EPI_RESIDUAL:
         if residual is None:
@@ -103,9 +118,9 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         if bias.numel() != N or not bias.is_contiguous():
             raise _lib.MovaB200Error("linear: bias must be a contiguous bf16 vector of N elements")
         bias_ptr = bias.data_ptr()
-    rc = _lib.load().mova_b200_linear_segk(x.data_ptr(), lda, seg_k, seg_stride, weight.data_ptr(), ldw, bias_ptr,
-                                           out.data_ptr(), ldc, M, N, K, epilogue, res_ptr, ldr, gate_ptr, float(scale),
-                                           cta_group, _stream())
+    rc = _lib.load().mova_b200_linear_ex(x.data_ptr(), lda, seg_k, seg_stride, weight.data_ptr(), ldw, bias_ptr,
+                                         out.data_ptr(), ldc, seg_n, c_seg_stride, M, N, K, epilogue, res_ptr, ldr,
+                                         gate_ptr, float(scale), cta_group, _stream())
     _lib.check(rc, "mova_b200_linear")
     return out
 
@@ -136,11 +151,19 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int,
             raise _lib.MovaB200Error("attention: bad `out`")
     lse = torch.empty(B, num_heads, Sq, dtype=torch.float32, device=q.device) if return_lse else None
     scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(D)
+    rec = _lib._TIMERS
+    if rec is not None:  # bench.py: per-launch device time of the dominant kernel, on the launching stream
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.load().mova_b200_attn_fwd(
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
         v.stride(1), out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr() if lse is not None else None, B, Sq,
         Skv, num_heads, D, float(scale), _stream())
     _lib.check(rc, "mova_b200_attn_fwd")
+    if rec is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        rec.append((e0, e1, B, Sq, Skv, num_heads, D))
     return (out, lse) if return_lse else out
 
 

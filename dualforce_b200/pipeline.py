@@ -1,0 +1,277 @@
+"""Drop-in for ``MOVA.forward_dual_tower_dit`` (mova/diffusion/pipelines/pipeline_mova.py:612-711) and the
+installer that swaps the B200 modules into an existing ``MOVA`` pipeline the way the reference's own
+``MOVA.replace_attention`` (pipeline_mova.py:124-148) swaps attention modules.
+
+``forward_dual_tower_dit`` keeps the reference signature.  With ``cp_mesh=None`` it is the reference loop
+(bridge -> video block -> audio block for the first min(layers) layers, then the remaining video blocks) on the
+fused kernels.  With a ``cp_mesh`` it runs the context-parallel design of :mod:`dualforce_b200.cp`: sharded video
+tokens, Ulysses all-to-all overlapped with the attention kernels on a side stream, replicated audio tower, LSE
+merge for the v2a bridge -- and returns the same full-length tensors as cp=1.
+"""
+from __future__ import annotations
+
+import types
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import cp as cpmod
+from . import ops, rope
+from .modules import ConditionalCrossAttentionBlock, DiTBlock, DualTowerConditionalBridge
+
+__all__ = ["forward_dual_tower_dit", "install", "CPRuntime"]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# context-parallel runtime
+# ----------------------------------------------------------------------------------------------------------------
+class CPRuntime:
+    """Process-group handle + the communication stream the all-to-alls are queued on."""
+
+    def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: int = 2):
+        self.group, self.rank, self.size, self.device = group, rank, size, device
+        self.head_groups = head_groups
+        self.comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+
+    @classmethod
+    def from_mesh(cls, cp_mesh, device: torch.device, head_groups: int = 2) -> "CPRuntime":
+        key = (id(cp_mesh), str(device), head_groups)
+        rt = _RUNTIMES.get(key)
+        if rt is None:
+            rt = cls(cp_mesh.get_group(), cp_mesh.get_local_rank(), cp_mesh.size(), device, head_groups)
+            _RUNTIMES[key] = rt
+        return rt
+
+
+_RUNTIMES = {}
+
+
+def _cp_weights(block: DiTBlock, plan: cpmod.UlyssesPlan):
+    """Destination-rank-major copies of the self-attention weights of ``block`` for ``plan`` (built once)."""
+    cache = getattr(block, "_cp_cache", None)
+    if cache is None:
+        cache = block._cp_cache = {}
+    key = (plan.cp, plan.groups, block.self_attn.q.weight.data_ptr())
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    sa = block.self_attn
+    dev = sa.q.weight.device
+    rows = plan.qkv_row_index().to(dev)
+    chan = plan.channel_index().to(dev)
+    w = torch.cat([sa.q.weight.data, sa.k.weight.data, sa.v.weight.data], dim=0).index_select(0, rows).contiguous()
+    b = torch.cat([sa.q.bias.data, sa.k.bias.data, sa.v.bias.data], dim=0).index_select(0, rows).contiguous()
+    nq = sa.norm_q.weight.data.index_select(0, chan).contiguous()
+    nk = sa.norm_k.weight.data.index_select(0, chan).contiguous()
+    wo = sa.o.weight.data.index_select(1, chan).contiguous()
+    cache.clear()
+    cache[key] = (w, b, nq, nk, wo)
+    return cache[key]
+
+
+def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor, gate: torch.Tensor,
+                       rt: CPRuntime, rows_per_rank: Sequence[int]) -> torch.Tensor:
+    """``x + gate * self_attn(h)`` for the local token chunk: QKV GEMM writing destination-rank-major, full-row
+    RMSNorm + RoPE on the segmented buffer, per head group {all-to-all, attention, all-to-all back} with the
+    exchanges on the communication stream, o-projection reading source-rank-major with the gated residual fused."""
+    sa = block.self_attn
+    plan = cpmod.UlyssesPlan(sa.num_heads, sa.head_dim, rt.size,
+                             cpmod.UlyssesPlan.pick_groups(sa.num_heads // rt.size, rt.head_groups))
+    w, b, nq, nk, wo = _cp_weights(block, plan)
+    Lc = h.shape[1]
+    G, cp, wd = plan.groups, plan.cp, plan.w
+    cos, sin = tables
+    send = ops.linear(h[0], w, b, out_segments=plan.nseg)  # [G*cp, Lc, 3*wd]
+    seg_stride = Lc * 3 * wd
+    ops.rmsnorm_rope_(send[0][:, 0:wd], nq, sa.norm_q.eps, head_dim=sa.head_dim, cos=cos, sin=sin,
+                      rope_mode=ops.ROPE_INTERLEAVED, segments=plan.nseg, seg_stride=seg_stride)
+    ops.rmsnorm_rope_(send[0][:, wd:2 * wd], nk, sa.norm_k.eps, head_dim=sa.head_dim, cos=cos, sin=sin,
+                      rope_mode=ops.ROPE_INTERLEAVED, segments=plan.nseg, seg_stride=seg_stride)
+    send = send.view(G, cp, Lc, 3 * wd)
+    main = torch.cuda.current_stream()
+    comm = rt.comm_stream
+    ready = torch.cuda.Event()
+    ready.record(main)
+    # every buffer is allocated on the compute stream; the side stream only fills it between two events
+    L = sum(rows_per_rank)
+    recv = [torch.empty(L, 3 * wd, dtype=torch.bfloat16, device=h.device) for _ in range(G)]
+    back = torch.empty(G, cp, Lc, wd, dtype=torch.bfloat16, device=h.device)
+    in_done = []
+    with torch.cuda.stream(comm):
+        comm.wait_event(ready)
+        for g in range(G):
+            cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
+            ev = torch.cuda.Event()
+            ev.record(comm)
+            in_done.append(ev)
+    outs, out_done = [], []
+    for g in range(G):
+        main.wait_event(in_done[g])
+        qkv = recv[g].unsqueeze(0)
+        o = ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg)  # [1, L, wd]
+        outs.append(o)
+        att = torch.cuda.Event()
+        att.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(att)
+            cpmod.gather_heads(o[0], rows_per_rank, rt.rank, rt.group, out=back[g])
+            ev = torch.cuda.Event()
+            ev.record(comm)
+            out_done.append(ev)
+    for ev in out_done:
+        main.wait_event(ev)
+    return ops.linear(back.view(G * cp, Lc, wd), wo, sa.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x[0], gate=gate,
+                      segments=plan.nseg).unsqueeze(0)
+
+
+def _video_block_cp(block: DiTBlock, x: torch.Tensor, context: torch.Tensor, t_mod: torch.Tensor, tables,
+                    rt: CPRuntime, rows_per_rank: Sequence[int]) -> torch.Tensor:
+    """DiTBlock.forward (wan_video_dit.py:275-291) on this rank's token chunk; only the self-attention communicates."""
+    mod = block.modulation_f32(t_mod)
+    ca = block.cross_attn
+    h = ops.layernorm(x, block.norm1.eps, shift=mod[0], scale=mod[1])
+    x = _self_attention_cp(block, h, tables, x, mod[2], rt, rows_per_rank)
+    h = ops.layernorm(x, block.norm3.eps, weight=block.norm3.weight, bias=block.norm3.bias, out=h)
+    a = ca.attend(h, context)
+    ops.linear(a, ca.o.weight, ca.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x, out=x)
+    ops.layernorm(x, block.norm2.eps, shift=mod[3], scale=mod[4], out=h)
+    u = ops.linear(h, block.ffn[0].weight, block.ffn[0].bias, epilogue=ops.EPI_GELU_TANH)
+    ops.linear(u, block.ffn[2].weight, block.ffn[2].bias, epilogue=ops.EPI_RESIDUAL, residual=x, gate=mod[5], out=x)
+    return x
+
+
+def _v2a_cp(cond: ConditionalCrossAttentionBlock, audio_x: torch.Tensor, x_loc: torch.Tensor, a_tables, v_tables_loc,
+            scale: float, rt: CPRuntime) -> torch.Tensor:
+    """v2a bridge direction with sharded video keys: local partial attention, all-gather of (o, lse), exact merge."""
+    inner = cond.inner
+    q = inner.project_q(audio_x, a_tables)
+    k, v = inner.project_kv(cond.normed_condition(x_loc), v_tables_loc)
+    o, lse = ops.attention(q, k, v, inner.num_heads, return_lse=True)
+    o_all = cpmod.all_gather_stack(o[0], rt.size, rt.group)      # [cp, L_a, d_a]
+    lse_all = cpmod.all_gather_stack(lse[0], rt.size, rt.group)  # [cp, H, L_a]
+    merged = ops.lse_merge(o_all, lse_all, inner.num_heads)
+    return ops.linear(merged.unsqueeze(0), inner.o.weight, inner.o.bias, epilogue=ops.EPI_RESIDUAL, residual=audio_x,
+                      scale=float(scale))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the path
+# ----------------------------------------------------------------------------------------------------------------
+def _check_modules(visual_dit, audio_dit, bridge) -> None:
+    for blk in list(visual_dit.blocks) + list(audio_dit.blocks):
+        if not isinstance(blk, DiTBlock):
+            raise TypeError("forward_dual_tower_dit needs dualforce_b200.DiTBlock modules; call dualforce_b200.install(pipe) "
+                            f"first (found {type(blk).__module__}.{type(blk).__name__})")
+    if not isinstance(bridge, DualTowerConditionalBridge):
+        raise TypeError("forward_dual_tower_dit needs a dualforce_b200.DualTowerConditionalBridge; call install(pipe)")
+
+
+@torch.no_grad()
+def forward_dual_tower_dit(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tensor,
+                           visual_context: torch.Tensor, audio_context: torch.Tensor, visual_t_mod: torch.Tensor,
+                           audio_t_mod: Optional[torch.Tensor], visual_freqs: torch.Tensor, audio_freqs: torch.Tensor,
+                           grid_size: Tuple[int, int, int], video_fps: float, condition_scale: Optional[float] = 1.0,
+                           a2v_condition_scale: Optional[float] = None, v2a_condition_scale: Optional[float] = None,
+                           cp_mesh=None):
+    """Same contract as pipeline_mova.py:612-711: returns full-length ``(visual_x, audio_x)`` hidden states.
+    ``self`` only needs ``audio_dit`` and ``dual_tower_bridge`` attributes (a ``MOVA`` pipeline after ``install``)."""
+    audio_dit, bridge = self.audio_dit, self.dual_tower_bridge
+    _check_modules(visual_dit, audio_dit, bridge)
+    if visual_x.shape[0] != 1 and cp_mesh is not None:
+        raise NotImplementedError("context parallelism with batch > 1 (MOVA runs CFG as two B=1 forwards)")
+    min_layers = min(len(visual_dit.blocks), len(audio_dit.blocks))
+    visual_layers = len(visual_dit.blocks)
+    assert visual_layers >= min_layers, "visual_layers must be greater than min_layers"
+
+    v_tab = rope.as_tables(visual_freqs)
+    a_tab = rope.as_tables(audio_freqs)
+    v_cs = a_cs = None
+    if bridge.apply_cross_rope:
+        # built (and memoised) in fp32: the reference rounds these tables to bf16 (interactionv2.py:236-237),
+        # which only adds noise relative to the fp32 oracle
+        v_pair, a_pair = bridge.build_aligned_freqs(video_fps=video_fps, grid_size=grid_size,
+                                                    audio_steps=audio_x.shape[1], device=visual_x.device,
+                                                    dtype=torch.float32)
+        v_cs, a_cs = rope.as_tables(v_pair), rope.as_tables(a_pair)
+
+    def scale_for(direct):
+        return bridge._scale(direct if direct is not None else condition_scale)
+
+    if cp_mesh is None:
+        for i in range(min_layers):
+            if bridge.should_interact(i, "a2v"):
+                visual_x, audio_x = bridge(i, visual_x, audio_x, x_freqs=v_cs, y_freqs=a_cs,
+                                           a2v_condition_scale=a2v_condition_scale,
+                                           v2a_condition_scale=v2a_condition_scale, condition_scale=condition_scale,
+                                           video_grid_size=grid_size)
+            visual_x = visual_dit.blocks[i](visual_x, visual_context, visual_t_mod, v_tab)
+            audio_x = audio_dit.blocks[i](audio_x, audio_context, audio_t_mod, a_tab)
+        for i in range(min_layers, visual_layers):
+            visual_x = visual_dit.blocks[i](visual_x, visual_context, visual_t_mod, v_tab)
+        return visual_x, audio_x
+
+    # ------------------------------ context parallel ------------------------------
+    rt = CPRuntime.from_mesh(cp_mesh, visual_x.device)
+    chunks = cpmod.seq_chunks(visual_x.shape[1], rt.size)
+    rows = [b - a for a, b in chunks]
+    s0, s1 = chunks[rt.rank]
+    x_loc = visual_x[:, s0:s1].contiguous()
+    v_tab_loc = (v_tab[0][s0:s1].contiguous(), v_tab[1][s0:s1].contiguous())
+    v_cs_loc = (v_cs[0][s0:s1].contiguous(), v_cs[1][s0:s1].contiguous()) if v_cs is not None else None
+    for i in range(min_layers):
+        if bridge.should_interact(i, "a2v"):
+            # a2v: local video queries x replicated audio keys -- no communication
+            new_v = bridge.audio_to_video_conditioners[str(i)].forward_residual(
+                x_loc, audio_x, v_cs_loc, a_cs, scale_for(a2v_condition_scale))
+            if bridge.should_interact(i, "v2a"):
+                audio_x = _v2a_cp(bridge.video_to_audio_conditioners[str(i)], audio_x, x_loc, a_cs, v_cs_loc,
+                                  scale_for(v2a_condition_scale), rt)
+            x_loc = new_v
+        x_loc = _video_block_cp(visual_dit.blocks[i], x_loc, visual_context, visual_t_mod, v_tab_loc, rt, rows)
+        audio_x = audio_dit.blocks[i](audio_x, audio_context, audio_t_mod, a_tab)  # replicated
+    for i in range(min_layers, visual_layers):
+        x_loc = _video_block_cp(visual_dit.blocks[i], x_loc, visual_context, visual_t_mod, v_tab_loc, rt, rows)
+    visual_full = cpmod.all_gather_cat(x_loc, rows, rt.group, dim=1)
+    return visual_full, audio_x
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# installer
+# ----------------------------------------------------------------------------------------------------------------
+def _swap_blocks(model) -> int:
+    n = 0
+    for i, blk in enumerate(model.blocks):
+        if not isinstance(blk, DiTBlock):
+            model.blocks[i] = DiTBlock.from_reference(blk)
+            n += 1
+    return n
+
+
+def install(pipe) -> int:
+    """Swap the B200 modules into a reference ``MOVA`` pipeline (or any object with ``video_dit``,
+    ``video_dit_2``, ``audio_dit``, ``dual_tower_bridge``) in place, sharing its parameters, and bind
+    ``pipe.forward_dual_tower_dit`` to the B200 path.  Returns the number of modules replaced -- the same idiom as
+    ``MOVA.replace_attention`` (pipeline_mova.py:124-148), which becomes unnecessary (and must not be called after
+    this): context parallelism is handled inside ``forward_dual_tower_dit`` from ``cp_mesh``.
+
+    Raises if the extension library is missing or the device is not sm_100 -- there is no fallback."""
+    from . import _lib
+
+    _lib.load()
+    if torch.cuda.is_available():
+        _lib.require_device(torch.cuda.current_device())
+    else:
+        raise _lib.MovaB200Error("dualforce_b200.install: no CUDA device (the B200 path has no CPU fallback)")
+    count = 0
+    for name in ("video_dit", "video_dit_2", "audio_dit"):
+        model = getattr(pipe, name, None)
+        if model is not None:
+            count += _swap_blocks(model)
+    bridge = getattr(pipe, "dual_tower_bridge", None)
+    if bridge is not None and not isinstance(bridge, DualTowerConditionalBridge):
+        pipe.dual_tower_bridge = DualTowerConditionalBridge.from_reference(bridge)
+        count += len(pipe.dual_tower_bridge.audio_to_video_conditioners) + len(
+            pipe.dual_tower_bridge.video_to_audio_conditioners)
+    pipe.forward_dual_tower_dit = types.MethodType(forward_dual_tower_dit, pipe)
+    return count

@@ -63,16 +63,19 @@ int mova_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, con
                      const float* gate, float scale, int cta_group, void* stream);
 
 /*
- * Same, with the A operand split along K into K/seg_k segments that live `seg_stride` elements apart:
- *   A(m, k) = A[(k / seg_k) * seg_stride + m * lda + (k % seg_k)],   seg_k % 64 == 0.
- * This is the layout an all-to-all leaves the attention output in under context parallelism
- * ([source rank][token][heads of that rank]); the o-projection reads it in place (mova/distributed, yunchang
- * LongContextAttention called from wan_video_dit.py:207 does a separate inverse all-to-all + permute instead).
+ * Same, with segmented operands for the context-parallel (Ulysses) layouts, so no pack / unpack copy is needed
+ * around the all-to-all (the reference's yunchang LongContextAttention, called from wan_video_dit.py:207, permutes
+ * and copies on both sides):
+ *   A(m, k) = A[(k / seg_k) * a_seg_stride + m * lda + (k % seg_k)]      seg_k % 64 == 0 or seg_k == K
+ *       -- what the inverse all-to-all delivers: [source rank][token][heads of that rank];
+ *   C(m, n) = C[(n / seg_n) * c_seg_stride + m * ldc + (n % seg_n)]      seg_n % 64 == 0 or seg_n == N
+ *       -- what the forward all-to-all sends: [destination rank][token][q|k|v heads of that rank]
+ *          (MOVA_EPI_RESIDUAL is not available with a segmented C).
  */
-int mova_b200_linear_segk(const void* A, int64_t lda, int seg_k, int64_t seg_stride, const void* W, int64_t ldw,
-                          const void* bias, void* C, int64_t ldc, int M, int N, int K, int epilogue,
-                          const void* residual, int64_t ldr, const float* gate, float scale, int cta_group,
-                          void* stream);
+int mova_b200_linear_ex(const void* A, int64_t lda, int seg_k, int64_t a_seg_stride, const void* W, int64_t ldw,
+                        const void* bias, void* C, int64_t ldc, int seg_n, int64_t c_seg_stride, int M, int N, int K,
+                        int epilogue, const void* residual, int64_t ldr, const float* gate, float scale,
+                        int cta_group, void* stream);
 
 /*
  * Non-causal softmax attention, head_dim 128: O = softmax(Q K^T * softmax_scale) V.
