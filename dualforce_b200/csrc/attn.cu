@@ -36,8 +36,8 @@ constexpr int AT_BAR_QFULL = 0;                        // [2]
 constexpr int AT_BAR_KVFULL = 2;                       // [NS]
 constexpr int AT_BAR_KVEMPTY = AT_BAR_KVFULL + AT_NS;  // [NS]
 constexpr int AT_BAR_SFULL = AT_BAR_KVEMPTY + AT_NS;   // [2]
-constexpr int AT_BAR_PREADY = AT_BAR_SFULL + 2;        // [2]
-constexpr int AT_BAR_ODONE = AT_BAR_PREADY + 2;        // [2]
+constexpr int AT_BAR_PREADY = AT_BAR_SFULL + 2;        // [tile][half of the key block] = [4]
+constexpr int AT_BAR_ODONE = AT_BAR_PREADY + 4;        // [2]
 constexpr int AT_NUM_BARS = AT_BAR_ODONE + 2;
 constexpr int AT_OFF_TMEM_PTR = AT_OFF_BARS + AT_NUM_BARS * 8;
 constexpr int AT_SMEM_BYTES = AT_OFF_TMEM_PTR + 16;
@@ -46,18 +46,40 @@ static_assert(AT_SMEM_BYTES <= 232448, "attention shared memory budget exceeded"
 constexpr uint32_t AT_TMEM_S = 0;    // + 128 * tile
 constexpr uint32_t AT_TMEM_O = 256;  // + 128 * tile
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+constexpr int AT_DEFAULT_EMU = 4;
 
 struct AttnParams {
   int Sq, Skv, H;
   float scale;       // softmax scale
   float scale_log2;  // scale * log2(e)
   float* lse;        // [B, H, Sq] or null
-  uint32_t v_lbo, v_sbo;
+  unsigned long long* trace;  // diagnostics (MOVA_ATTN_TRACE): 3 regions of 4096 (clock << 8 | event) records
 };
 
 __device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
 __device__ __forceinline__ void setmaxnreg_dec_88() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;"); }
 
+// 2^x for a pair of scores on the FMA/ALU pipes instead of the 16-lane/clk MUFU unit (which at head_dim 128 is as
+// busy as the tensor cores): round x to the nearest integer n with the 1.5*2^23 trick, evaluate a degree-3 minimax
+// polynomial of 2^r on r = x - n in [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P) with
+// packed f32x2 instructions, then add n to the exponent field.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(r, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, r, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, r, make_float2(0.9999280572f, 0.9999280572f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+
+// EMU: how many of every 16 score pairs take the polynomial path (0 = all MUFU, 8 = half and half)
+template <int EMU, bool TRACE>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -70,6 +92,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int row_base = blockIdx.x * 256;
   const int nt = (row_base + 128 < p.Sq) ? 2 : 1;  // live query tiles of this CTA
   const int n_kv = (p.Skv + 127) >> 7;
+  // event trace of CTA (0,0,0): softmax thread 0 of each tile and the tcgen05 issuer
+  int trace_n = 0;
+  const bool tracing = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && p.trace != nullptr;
+  auto ev = [&](int region, int id) {
+    if (TRACE && tracing && trace_n < 4096)
+      p.trace[region * 4096 + trace_n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(id);
+  };
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bars = smem_base + AT_OFF_BARS;
@@ -89,7 +118,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(AT_BAR_SFULL + i), 1);
-      mbar_init(bar(AT_BAR_PREADY + i), 4);  // one arrive per softmax warp
+      mbar_init(bar(AT_BAR_PREADY + 2 * i), 4);  // one arrive per softmax warp
+      mbar_init(bar(AT_BAR_PREADY + 2 * i + 1), 4);
       mbar_init(bar(AT_BAR_ODONE + i), 1);
     }
     fence_barrier_init();
@@ -118,24 +148,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(bar(AT_BAR_SFULL + tile), j & 1);
         tc_fence_after();
+        if ((threadIdx.x & 127) == 0) ev(tile, 1);
         uint32_t s[128];
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld_x32(t_s + q * 32, reinterpret_cast<uint32_t(&)[32]>(s[q * 32]));
         tmem_wait_ld();
+        if ((threadIdx.x & 127) == 0) ev(tile, 2);
         if (j == n_kv - 1 && tail < 128) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
             if (i >= tail) s[i] = 0xff800000u;  // -inf
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        // 8 independent chains: the 3-input FMNMX has a long dependent-issue latency (4 chains cost ~420 cycles)
+        float mx[8];
 #pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        for (int k = 0; k < 8; ++k) mx[k] = fmaxf(__uint_as_float(s[k]), __uint_as_float(s[k + 8]));
+#pragma unroll
+        for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mx[k] = fmaxf(mx[k], fmaxf(__uint_as_float(s[i + k]), __uint_as_float(s[i + k + 8])));
         }
-        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+        const float m_new = fmaxf(m_used, fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                                fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7]))));
         if (j == 0) {
           m_used = m_new;  // nothing accumulated yet
         } else {
@@ -157,34 +192,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_wait_st();
           }
         }
+        if ((threadIdx.x & 127) == 0) ev(tile, 3);
         const float neg = -m_used * c;
+        const float2 c2 = make_float2(c, c);
+        const float2 neg2 = make_float2(neg, neg);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          if (q == 2) {
+            // first half of P (keys 0..63) is complete: let the issuer start P.V on it while the second half is
+            // still in the exponential unit
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(AT_BAR_PREADY + 2 * tile));
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(s[q * 32 + 2 * e]), c, neg));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(s[q * 32 + 2 * e + 1]), c, neg));
-            s[q * 32 + 2 * e] = __float_as_uint(p0);
-            s[q * 32 + 2 * e + 1] = __float_as_uint(p1);
-            pk[e] = pack_bf16x2(p0, p1);
+            const float2 x = __ffma2_rn(
+                make_float2(__uint_as_float(s[q * 32 + 2 * e]), __uint_as_float(s[q * 32 + 2 * e + 1])), c2, neg2);
+            float2 pv;
+            if (((e + 1) * EMU) / 16 > (e * EMU) / 16) {  // evenly spread, resolved at compile time
+              pv = exp2_poly2(x);
+            } else {
+              pv.x = fast_exp2(x.x);
+              pv.y = fast_exp2(x.y);
+            }
+            s[q * 32 + 2 * e] = __float_as_uint(pv.x);
+            s[q * 32 + 2 * e + 1] = __float_as_uint(pv.y);
+            pk[e] = pack_bf16x2(pv.x, pv.y);
           }
           tmem_st_x16(t_s + q * 16, pk);
         }
+        if ((threadIdx.x & 127) == 0) ev(tile, 4);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(AT_BAR_PREADY + tile));
+        if (lane == 0) mbar_arrive(bar(AT_BAR_PREADY + 2 * tile + 1));
+        if ((threadIdx.x & 127) == 0) ev(tile, 5);
         // row sum, off the critical path
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          a0 += __uint_as_float(s[i]);
-          a1 += __uint_as_float(s[i + 1]);
-          a2 += __uint_as_float(s[i + 2]);
-          a3 += __uint_as_float(s[i + 3]);
+        for (int i = 0; i < 128; i += 8) {
+          a0 = __fadd2_rn(a0, make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+          a1 = __fadd2_rn(a1, make_float2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+          a2 = __fadd2_rn(a2, make_float2(__uint_as_float(s[i + 4]), __uint_as_float(s[i + 5])));
+          a3 = __fadd2_rn(a3, make_float2(__uint_as_float(s[i + 6]), __uint_as_float(s[i + 7])));
         }
-        l += (a0 + a1) + (a2 + a3);
+        a0 = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
+        l += a0.x + a0.y;
       }
 
       // ---- epilogue: O / l -> bf16 -> swizzled smem (dead Q tile) -> TMA store ----
@@ -246,75 +302,89 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     } else if (warp_idx == 9) {
       // =========================== tcgen05 issuer ===========================
-      if (elect_one()) {
-        constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
-        constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 0, 1);
-        auto issue_qk = [&](int tile, uint32_t kbase) {
-          const uint32_t qb = smem_base + AT_OFF_Q + tile * AT_TILE_BYTES;
+      // The whole warp walks the schedule (so addresses and descriptors live in uniform registers); one elected
+      // lane issues the MMAs and commits.
+      constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 0, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      auto issue_qk = [&](int tile, uint32_t kbase) {
+        const uint64_t qd = umma_desc_k_sw128(smem_base + AT_OFF_Q + tile * AT_TILE_BYTES);
+        const uint64_t kd = umma_desc_k_sw128(kbase);
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t off = (ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32;
-            umma_ss<1>(tmem_base + AT_TMEM_S + tile * 128, umma_desc_k_sw128(qb + off), umma_desc_k_sw128(kbase + off),
-                       IDESC_QK, ks > 0 ? 1u : 0u);
+            const uint32_t off16 = ((ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32) >> 4;
+            umma_ss<1>(tmem_u + AT_TMEM_S + tile * 128, qd + off16, kd + off16, IDESC_QK, ks > 0 ? 1u : 0u);
           }
-        };
-        auto issue_pv = [&](int tile, uint32_t vbase, bool acc) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            umma_ts(tmem_base + AT_TMEM_O + tile * 128, tmem_base + AT_TMEM_S + tile * 128 + ks * 8,
-                    umma_desc_mn_sw128(vbase + ks * 2048, p.v_lbo, p.v_sbo), IDESC_PV, (acc || ks > 0) ? 1u : 0u);
-          }
-        };
-        uint32_t slot = 0, phase = 0;
-        auto next_slot = [&]() { if (++slot == AT_NS) { slot = 0; phase ^= 1; } };
-        auto slot_addr = [&](uint32_t s_) { return smem_base + AT_OFF_KV + s_ * AT_TILE_BYTES; };
-
-        // S(0) of both tiles
-        mbar_wait(bar(AT_BAR_QFULL + 0), 0);
-        mbar_wait(bar(AT_BAR_KVFULL + slot), phase);
-        tc_fence_after();
-        issue_qk(0, slot_addr(slot));
-        umma_commit(bar(AT_BAR_SFULL + 0));
-        if (nt == 2) {
-          mbar_wait(bar(AT_BAR_QFULL + 1), 0);
-          tc_fence_after();
-          issue_qk(1, slot_addr(slot));
-          umma_commit(bar(AT_BAR_SFULL + 1));
+          umma_commit(bar(AT_BAR_SFULL + tile));
         }
-        umma_commit(bar(AT_BAR_KVEMPTY + slot));
-        next_slot();
+        __syncwarp();
+      };
+      // P.V over keys [64*half, 64*half + 64) of the block
+      auto issue_pv_half = [&](int tile, uint32_t vbase, int half, bool acc) {
+        const uint64_t vd = umma_desc_mn_sw128(vbase + half * 8192, AT_HALF_BYTES, 1024);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            umma_ts(tmem_u + AT_TMEM_O + tile * 128, tmem_u + AT_TMEM_S + tile * 128 + half * 32 + ks * 8,
+                    vd + ((ks * 2048) >> 4), IDESC_PV, (acc || half > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint32_t b_) {
+        if (elect_one()) umma_commit(b_);
+        __syncwarp();
+      };
+      uint32_t slot = 0, phase = 0;
+      auto next_slot = [&]() { if (++slot == AT_NS) { slot = 0; phase ^= 1; } };
+      auto slot_addr = [&](uint32_t s_) { return smem_base + AT_OFF_KV + s_ * AT_TILE_BYTES; };
 
-        for (int j = 0; j < n_kv; ++j) {
-          const bool last = (j == n_kv - 1);
-          const uint32_t vslot = slot;
-          mbar_wait(bar(AT_BAR_KVFULL + vslot), phase);
-          next_slot();
-          const uint32_t kslot = slot;
-          mbar_wait(bar(AT_BAR_PREADY + 0), j & 1);
+      // S(0) of both tiles
+      mbar_wait(bar(AT_BAR_QFULL + 0), 0);
+      mbar_wait(bar(AT_BAR_KVFULL + slot), phase);
+      tc_fence_after();
+      issue_qk(0, slot_addr(slot));
+      if (nt == 2) {
+        mbar_wait(bar(AT_BAR_QFULL + 1), 0);
+        tc_fence_after();
+        issue_qk(1, slot_addr(slot));
+      }
+      commit(bar(AT_BAR_KVEMPTY + slot));
+      next_slot();
+
+      for (int j = 0; j < n_kv; ++j) {
+        const bool last = (j == n_kv - 1);
+        const uint32_t vslot = slot;
+        mbar_wait(bar(AT_BAR_KVFULL + vslot), phase);
+        next_slot();
+        const uint32_t kslot = slot;
+        const uint32_t kphase = phase;
+        for (int tile = 0; tile < nt; ++tile) {
+          // one barrier per half of P: a single two-phase barrier would let the softmax run two phases ahead of
+          // this warp, which a parity wait cannot tell apart from "not there yet"
+          mbar_wait(bar(AT_BAR_PREADY + 2 * tile), j & 1);
           tc_fence_after();
-          issue_pv(0, slot_addr(vslot), j > 0);
-          if (last) umma_commit(bar(AT_BAR_ODONE + 0));
+          if (tile == 0) ev(2, 10); else ev(2, 11);
+          issue_pv_half(tile, slot_addr(vslot), 0, j > 0);
+          mbar_wait(bar(AT_BAR_PREADY + 2 * tile + 1), j & 1);
+          tc_fence_after();
+          issue_pv_half(tile, slot_addr(vslot), 1, true);
+          if (tile == 0) ev(2, 12); else ev(2, 13);
+          if (last) commit(bar(AT_BAR_ODONE + tile));
           if (!last) {
-            mbar_wait(bar(AT_BAR_KVFULL + kslot), phase);
-            tc_fence_after();
-            issue_qk(0, slot_addr(kslot));
-            umma_commit(bar(AT_BAR_SFULL + 0));
-          }
-          if (nt == 2) {
-            mbar_wait(bar(AT_BAR_PREADY + 1), j & 1);
-            tc_fence_after();
-            issue_pv(1, slot_addr(vslot), j > 0);
-            if (last) umma_commit(bar(AT_BAR_ODONE + 1));
-          }
-          umma_commit(bar(AT_BAR_KVEMPTY + vslot));
-          if (!last) {
-            if (nt == 2) {
-              issue_qk(1, slot_addr(kslot));
-              umma_commit(bar(AT_BAR_SFULL + 1));
+            if (tile == 0) {
+              mbar_wait(bar(AT_BAR_KVFULL + kslot), kphase);
+              tc_fence_after();
             }
-            umma_commit(bar(AT_BAR_KVEMPTY + kslot));
-            next_slot();
+            issue_qk(tile, slot_addr(kslot));
+            if (tile == 0) ev(2, 14); else ev(2, 15);
           }
+        }
+        commit(bar(AT_BAR_KVEMPTY + vslot));
+        if (!last) {
+          commit(bar(AT_BAR_KVEMPTY + kslot));
+          next_slot();
         }
       }
     }
@@ -325,6 +395,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp_idx == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
+template <int EMU, bool TRACE>
+static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+                       const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
+  auto kernel = attn_fwd_kernel<EMU, TRACE>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  MV_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    MV_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  MV_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace mv
@@ -366,19 +452,44 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.lse = lse;
-  p.v_lbo = AT_HALF_BYTES;  // distance between the two 64-wide head-dim panels of a V tile
-  p.v_sbo = 1024;           // distance between 8-key groups inside a panel
 
   debug_attach();
-  static bool configured[64] = {false};
-  int dev = 0;
-  MV_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    MV_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+  // share of exponentials evaluated by polynomial (in 16ths of the pairs); MOVA_ATTN_EMU overrides for tuning
+  static int emu = -1;
+  if (emu < 0) {
+    const char* e = getenv("MOVA_ATTN_EMU");
+    emu = e ? atoi(e) : AT_DEFAULT_EMU;
   }
   dim3 grid((Sq + 255) / 256, H, B);
-  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmO, p);
-  MV_CHECK_CUDA(cudaGetLastError());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // diagnostics only: MOVA_ATTN_TRACE=<file> records the event timeline of CTA (0,0,0) of every launch (synchronous!)
+  static const char* trace_path = getenv("MOVA_ATTN_TRACE");
+  p.trace = nullptr;
+  if (trace_path != nullptr) {
+    static unsigned long long* tbuf = nullptr;
+    if (tbuf == nullptr) MV_CHECK_CUDA(cudaMalloc(&tbuf, 3 * 4096 * sizeof(unsigned long long)));
+    MV_CHECK_CUDA(cudaMemsetAsync(tbuf, 0, 3 * 4096 * sizeof(unsigned long long), st));
+    p.trace = tbuf;
+    int rc = (emu == 0) ? launch_attn<0, true>(grid, st, tmQ, tmK, tmV, tmO, p)
+                        : launch_attn<AT_DEFAULT_EMU, true>(grid, st, tmQ, tmK, tmV, tmO, p);
+    if (rc != 0) return rc;
+    MV_CHECK_CUDA(cudaStreamSynchronize(st));
+    static unsigned long long host[3 * 4096];
+    MV_CHECK_CUDA(cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "wb");
+    if (f != nullptr) {
+      fwrite(host, 1, sizeof(host), f);
+      fclose(f);
+    }
+    return 0;
+  }
+  switch (emu) {
+    case 0: return launch_attn<0, false>(grid, st, tmQ, tmK, tmV, tmO, p);
+    case 2: return launch_attn<2, false>(grid, st, tmQ, tmK, tmV, tmO, p);
+    case 4: return launch_attn<4, false>(grid, st, tmQ, tmK, tmV, tmO, p);
+    case 6: return launch_attn<6, false>(grid, st, tmQ, tmK, tmV, tmO, p);
+    case 8: return launch_attn<8, false>(grid, st, tmQ, tmK, tmV, tmO, p);
+    default: MV_REQUIRE(false, "mova_b200_attn_fwd: MOVA_ATTN_EMU must be one of 0,2,4,6,8 (got %d)", emu);
+  }
   return 0;
 }
