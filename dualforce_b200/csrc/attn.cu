@@ -12,11 +12,20 @@
 //     its S tile and consumed straight from TMEM as the A operand of the P.V MMA.
 //   * K and V tiles (128 keys x 128 dims, 32 KB) stream through one 5-slot ring in the order
 //     K0 V0 K1 V1 ...; V is used as an MN-major B operand, so no transpose is ever made.
-//   * the issuer interleaves  PV0(j) QK0(j+1) PV1(j) QK1(j+1)  so one tile's softmax overlaps the other
-//     tile's MMAs; tcgen05 executes in issue order, which is what makes the S/P aliasing safe.
-//   * online softmax in the exp2 domain with lazy rescaling: the running maximum baked into O and l is
-//     only advanced when the new block maximum exceeds it by more than 2^8, so O is touched rarely.
+//   * the issuer warp walks the schedule warp-uniformly (descriptors in uniform registers, one elected lane
+//     issues):  PV0(j) QK0(j+1) PV1(j) QK1(j+1), so one tile's softmax overlaps the other tile's MMAs; tcgen05
+//     executes in issue order, which is what makes the S/P aliasing safe.
+//   * P is released to the tensor core in two halves (keys 0-63, 64-127; one mbarrier each): the first half of
+//     P.V runs while the second half of the row is still in the exponential unit.
+//   * online softmax in the exp2 domain, packed f32x2 math, lazy rescaling: the running maximum baked into O and l
+//     is only advanced when the new block maximum exceeds it by more than 2^8, so O is touched rarely; a
+//     configurable share of the exponentials runs as a polynomial on the FMA pipe (MUFU relief).
 //   * epilogue: O/l -> bf16 -> swizzled smem (the dead Q tile) -> TMA store (rows >= Sq are clipped).
+//
+// Measured alternatives that LOST on B200 (kept in git history): 64-key sub-blocks with double-buffered
+// score tiles (1045 TFLOP/s: the P-over-S aliasing still chains S(i+1) to P(i-1), and the per-sub-block fixed
+// costs double), the same with a software-pipelined softmax (1042), turn-taking between the two softmax
+// warpgroups on the MUFU phase (938).  This kernel: 1271-1279 TFLOP/s at S = 43120, 40 heads.
 #include <stdlib.h>
 
 #include "common.cuh"
