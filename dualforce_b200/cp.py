@@ -149,6 +149,6 @@ def all_gather_cat(x: torch.Tensor, rows_per_rank: Sequence[int], group: Optiona
 def all_gather_stack(x: torch.Tensor, cp: int, group: Optional[dist.ProcessGroup]) -> torch.Tensor:
     """``[cp, *x.shape]`` stack of every rank's ``x`` (partial outputs / LSEs of the sharded v2a attention)."""
     x = x.contiguous()
-    buf = torch.empty((cp,) + tuple(x.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(buf, x, group=group)
-    return buf
+    flat = torch.empty((cp * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(flat, x, group=group)  # concatenated along dim 0 (the form every backend accepts)
+    return flat.view((cp,) + tuple(x.shape))

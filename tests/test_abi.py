@@ -1,0 +1,49 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/mova_b200.h declares (no compute)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "mova_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mova_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    from dualforce_b200 import _lib
+
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 10
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in include/mova_b200.h but not exported by libmova_b200.so"
+    assert set(_lib.SIGNATURES) <= set(syms), "python binding names a symbol the header does not declare"
+    assert lib.mova_b200_abi_version() == _lib.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must be rejected loudly: the product path has no CPU implementation."""
+    import torch
+
+    import dualforce_b200 as B
+
+    x = torch.zeros(4, 8, dtype=torch.bfloat16)
+    with pytest.raises(B.MovaB200Error):
+        B.ops.linear(x, x)
+    with pytest.raises(B.MovaB200Error):
+        B.ops.attention(x[None], x[None], x[None], 1)
+    if not torch.cuda.is_available():
+        with pytest.raises(B.MovaB200Error):
+            B.install(object())
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dualforce_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "mova_oracle" not in src and "ref_loader" not in src, f"{fn} references the test oracle"
