@@ -348,7 +348,7 @@ def run_b200_arm(args):
         tf = sel[0][1] / (avg_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "attn_traffic.json")
-        if os.path.exists(tpath):
+        if world == 1 and os.path.exists(tpath):  # the ncu capture is of the 40-head single-GPU launch
             with open(tpath) as fh:
                 traffic = json.load(fh).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": "attn_fwd_kernel (video self-attention, L_v x L_v, %d heads/launch)" % sel_heads(attn_events, L_v),

@@ -35,7 +35,10 @@ CP_CFG = dict(O.TINY_CFG, visual_dim=512, visual_heads=4, visual_ffn=768, grid_s
 
 
 def run_check(rank: int, world: int, cfg=None, seed: int = 77):
-    cfg = cfg or CP_CFG
+    if cfg is None:
+        cfg = CP_CFG
+        if cfg["visual_heads"] % world:  # e.g. 8 ranks: 8 video heads (1024 channels), 60 video tokens over 8 ranks
+            cfg = dict(cfg, visual_heads=world, visual_dim=128 * world, visual_ffn=256 * world)
     torch.cuda.set_device(rank % torch.cuda.device_count())
     Pv, Pa, Pb, inp = O.make_case(cfg, seed)
     Pv, Pa, Pb, inp = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb), bf16_round(inp)
