@@ -25,7 +25,9 @@
 // Measured alternatives that LOST on B200 (kept in git history): 64-key sub-blocks with double-buffered
 // score tiles (1045 TFLOP/s: the P-over-S aliasing still chains S(i+1) to P(i-1), and the per-sub-block fixed
 // costs double), the same with a software-pipelined softmax (1042), turn-taking between the two softmax
-// warpgroups on the MUFU phase (938).  This kernel: 1271-1279 TFLOP/s at S = 43120, 40 heads.
+// warpgroups on the MUFU phase (938), two threads per query row / 16 softmax warps (1178: the phase lengths did not
+// move, i.e. they are set by shared units -- MUFU 16 lanes/clk, TMEM read port -- not by per-thread issue).
+// This kernel: 1271-1279 TFLOP/s at S = 43120, 40 heads.
 #include <stdlib.h>
 
 #include "common.cuh"
