@@ -20,7 +20,7 @@ from . import cp as cpmod
 from . import ops, rope
 from .modules import ConditionalCrossAttentionBlock, DiTBlock, DualTowerConditionalBridge
 
-__all__ = ["forward_dual_tower_dit", "install", "CPRuntime"]
+__all__ = ["forward_dual_tower_dit", "install", "CPRuntime", "GraphedForward"]
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -168,7 +168,7 @@ def _check_modules(visual_dit, audio_dit, bridge) -> None:
 
 
 @torch.no_grad()
-def forward_dual_tower_dit(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tensor,
+def _forward_eager(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tensor,
                            visual_context: torch.Tensor, audio_context: torch.Tensor, visual_t_mod: torch.Tensor,
                            audio_t_mod: Optional[torch.Tensor], visual_freqs: torch.Tensor, audio_freqs: torch.Tensor,
                            grid_size: Tuple[int, int, int], video_fps: float, condition_scale: Optional[float] = 1.0,
@@ -236,6 +236,72 @@ def forward_dual_tower_dit(self, visual_dit, visual_x: torch.Tensor, audio_x: to
     return visual_full, audio_x
 
 
+class GraphedForward:
+    """CUDA-graph replay of the whole forward for one set of argument shapes.
+
+    One forward is ~1600 kernel launches; the 403-token audio tower and the bridge's small kernels are launch-bound
+    (each runs for a few microseconds), which shows at cp = 8 where a video layer is down to ~8 ms.  Capturing the
+    launches once (TMA descriptors, NCCL all-to-alls on the side stream and all) and replaying the graph removes the
+    host from the loop.  Inputs are copied into static buffers before the replay, outputs are cloned after it, so
+    the caller sees ordinary tensors; RoPE tables are rebuilt inside the graph from the (static) complex inputs."""
+
+    def __init__(self, owner, visual_dit, tensors: dict, statics: dict, cp_mesh):
+        self.static_in = {k: v.clone() for k, v in tensors.items()}
+        self.statics = statics
+        self.cp_mesh = cp_mesh
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        rope.set_cache(False)  # table conversions must be recorded as graph nodes, not served from the memo
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up: packs weights, configures kernels, builds the NCCL channels
+                    _forward_eager(owner, visual_dit, **self.static_in, **statics, cp_mesh=cp_mesh)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_out = _forward_eager(owner, visual_dit, **self.static_in, **statics, cp_mesh=cp_mesh)
+        finally:
+            rope.set_cache(True)
+
+    def __call__(self, tensors: dict):
+        for k, v in tensors.items():
+            self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return tuple(t.clone() for t in self.static_out)
+
+
+_TENSOR_ARGS = ("visual_x", "audio_x", "visual_context", "audio_context", "visual_t_mod", "audio_t_mod", "visual_freqs",
+                "audio_freqs")
+
+
+@torch.no_grad()
+def forward_dual_tower_dit(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tensor,
+                           visual_context: torch.Tensor, audio_context: torch.Tensor, visual_t_mod: torch.Tensor,
+                           audio_t_mod: Optional[torch.Tensor], visual_freqs: torch.Tensor, audio_freqs: torch.Tensor,
+                           grid_size: Tuple[int, int, int], video_fps: float, condition_scale: Optional[float] = 1.0,
+                           a2v_condition_scale: Optional[float] = None, v2a_condition_scale: Optional[float] = None,
+                           cp_mesh=None):
+    """Drop-in for ``MOVA.forward_dual_tower_dit`` (pipeline_mova.py:612-711), same arguments and return value.
+    Runs eagerly, or -- when ``install(pipe, cuda_graph=True)`` / ``pipe.mova_b200_cuda_graph = True`` -- as a CUDA
+    graph captured on first use per argument-shape signature."""
+    statics = dict(grid_size=tuple(int(g) for g in grid_size), video_fps=float(video_fps),
+                   condition_scale=condition_scale, a2v_condition_scale=a2v_condition_scale,
+                   v2a_condition_scale=v2a_condition_scale)
+    tensors = dict(visual_x=visual_x, audio_x=audio_x, visual_context=visual_context, audio_context=audio_context,
+                   visual_t_mod=visual_t_mod, audio_t_mod=audio_t_mod, visual_freqs=visual_freqs, audio_freqs=audio_freqs)
+    if not getattr(self, "mova_b200_cuda_graph", False):
+        return _forward_eager(self, visual_dit, **tensors, **statics, cp_mesh=cp_mesh)
+    cache = self.__dict__.setdefault("_mova_b200_graphs", {})
+    key = (id(visual_dit), id(cp_mesh), tuple(sorted(statics.items())),
+           tuple((k, tuple(v.shape), v.dtype, str(v.device)) for k, v in tensors.items()))
+    runner = cache.get(key)
+    if runner is None:
+        runner = cache[key] = GraphedForward(self, visual_dit, tensors, statics, cp_mesh)
+    return runner(tensors)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # installer
 # ----------------------------------------------------------------------------------------------------------------
@@ -248,7 +314,7 @@ def _swap_blocks(model) -> int:
     return n
 
 
-def install(pipe) -> int:
+def install(pipe, cuda_graph: bool = False) -> int:
     """Swap the B200 modules into a reference ``MOVA`` pipeline (or any object with ``video_dit``,
     ``video_dit_2``, ``audio_dit``, ``dual_tower_bridge``) in place, sharing its parameters, and bind
     ``pipe.forward_dual_tower_dit`` to the B200 path.  Returns the number of modules replaced -- the same idiom as
@@ -274,4 +340,5 @@ def install(pipe) -> int:
         count += len(pipe.dual_tower_bridge.audio_to_video_conditioners) + len(
             pipe.dual_tower_bridge.video_to_audio_conditioners)
     pipe.forward_dual_tower_dit = types.MethodType(forward_dual_tower_dit, pipe)
+    pipe.mova_b200_cuda_graph = bool(cuda_graph)
     return count

@@ -20,11 +20,23 @@ _CACHE: Dict[tuple, tuple] = {}
 _CACHE_MAX = 16
 
 
+_ENABLED = True
+
+
+def set_cache(enabled: bool) -> None:
+    """Disable the memo while a CUDA graph is being captured: the conversions must become graph nodes that re-run on
+    every replay (the static input buffers keep their address but not their content)."""
+    global _ENABLED
+    _ENABLED = bool(enabled)
+
+
 def _key(t: torch.Tensor) -> tuple:
     return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version, str(t.device))
 
 
 def _remember(key: tuple, sources: tuple, value):
+    if not _ENABLED:
+        return value
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (sources, value)
@@ -40,7 +52,7 @@ def tables_from_complex(freqs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor
     if not torch.is_complex(freqs):
         raise TypeError(f"expected a complex RoPE table, got {freqs.dtype}")
     key = ("c",) + _key(freqs)
-    hit = _CACHE.get(key)
+    hit = _CACHE.get(key) if _ENABLED else None
     if hit is not None:
         return hit[1]
     f = freqs.reshape(freqs.shape[0], -1)
@@ -52,7 +64,7 @@ def tables_from_complex(freqs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor
 def tables_from_cos_sin(cos: torch.Tensor, sin: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """``[1, L, 128]`` (any float dtype) -> contiguous fp32 ``[L, 128]`` pair."""
     key = ("r",) + _key(cos) + _key(sin)
-    hit = _CACHE.get(key)
+    hit = _CACHE.get(key) if _ENABLED else None
     if hit is not None:
         return hit[1]
     src = (cos, sin)
