@@ -71,15 +71,16 @@ def run_reference(cfg, seed):
     # CP helpers (functional.py:55-111) on the audio tokens, 4 ranks: ragged last chunk
     for r in range(4):
         out[f"sp_split_r{r}"] = R.functional._sp_split_tensor(inp["audio_x"], sp_size=4, sp_rank=r)[0]
-    return {k: v.detach().numpy() for k, v in out.items()}, O.checksum(Pv, Pa, Pb, inp)
+    keys = {"dit_block": sorted(vis.blocks[0].state_dict().keys()), "bridge": sorted(bridge.state_dict().keys())}
+    return {k: v.detach().numpy() for k, v in out.items()}, O.checksum(Pv, Pa, Pb, inp), keys
 
 
 def main():
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     for name, cfg, seed in (("tiny_dual_tower", O.TINY_CFG, 1234),):
-        arrays, csum = run_reference(cfg, seed)
-        meta = dict(cfg=cfg, seed=seed, checksum=csum, torch=torch.__version__,
+        arrays, csum, keys = run_reference(cfg, seed)
+        meta = dict(cfg=cfg, seed=seed, checksum=csum, torch=torch.__version__, reference_state_dict_keys=keys,
                     source="reference modules from /root/reference run in fp32 on CPU by oracle/make_golden.py")
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrays)
         with open(os.path.join(out_dir, name + ".json"), "w") as f:

@@ -14,7 +14,7 @@ def test_full_path_matches_reference(seed, grid, audio_len):
     import make_golden
 
     cfg = dict(O.TINY_CFG, grid_size=grid, audio_len=audio_len)
-    arrays, _ = make_golden.run_reference(cfg, seed)
+    arrays, _, _ = make_golden.run_reference(cfg, seed)
     Pv, Pa, Pb, inp = O.make_case(cfg, seed)
     fv, fa = O.forward_dual_tower_dit(Pv, Pa, Pb, cfg, inp["visual_x"], inp["audio_x"], inp["visual_context"],
                                       inp["audio_context"], inp["visual_t_mod"], inp["audio_t_mod"], inp["visual_freqs"],
