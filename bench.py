@@ -173,7 +173,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -424,7 +424,7 @@ def run_b200_arm(args):
             sec = run()
             line["cpu_baseline"] = {"value": 1.0 / (sec * scale), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": CPU_SAMPLE_TEXT, "sample_seconds": sec}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -444,6 +444,27 @@ def sel_heads(events, L_v):
     return 0
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout clean for the ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    chatter) is sent to stderr; emit() writes the result to the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -457,6 +478,7 @@ def main():
     ap.add_argument("--cuda-graph", type=int, default=None,
                     help="1: replay the forward as a CUDA graph, 0: eager launches (default)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
