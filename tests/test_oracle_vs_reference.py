@@ -35,3 +35,71 @@ def test_rope_tables_match_reference():
     L = 21
     ref_a = torch.cat([fa[0][:L].view(L, -1), fa[1][:L].view(L, -1), fa[2][:L].view(L, -1)], dim=-1).reshape(L, 1, -1)
     assert torch.equal(O.audio_freqs(128, L), ref_a)
+
+
+def test_first_frame_bias_tables_match_reference():
+    R = ref_loader.load()
+    bridge = R.interactionv2.DualTowerConditionalBridge(visual_layers=2, audio_layers=2, visual_hidden_dim=256,
+                                                        audio_hidden_dim=128, audio_fps=50.0, head_dim=128,
+                                                        interaction_strategy="full", apply_cross_rope=True,
+                                                        apply_first_frame_bias_in_rope=True)
+    ref_v, ref_a = bridge.build_aligned_freqs(video_fps=24.0, grid_size=(5, 2, 3), audio_steps=17,
+                                              device=torch.device("cpu"), dtype=torch.float32)
+    got_v, got_a = O.build_aligned_freqs(24.0, (5, 2, 3), 17, 50.0, 128, apply_first_frame_bias=True)
+    for g, r in zip(got_v + got_a, ref_v + ref_a):
+        assert (g - r).abs().max() < 1e-6
+    # and the B200 module's own builder (pure torch, runs on CPU)
+    import dualforce_b200 as B
+
+    mine = B.DualTowerConditionalBridge(visual_layers=2, audio_layers=2, visual_hidden_dim=256, audio_hidden_dim=128,
+                                        audio_fps=50.0, head_dim=128, interaction_strategy="full", apply_cross_rope=True,
+                                        apply_first_frame_bias_in_rope=True)
+    m_v, m_a = mine.build_aligned_freqs(24.0, (5, 2, 3), 17, device=torch.device("cpu"), dtype=torch.float32)
+    for g, r in zip(m_v + m_a, ref_v + ref_a):
+        assert (g - r).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("strategy,nv,na", [("shallow_focus", 7, 6), ("distributed", 5, 4), ("custom", 4, 3)])
+def test_sparse_interaction_strategies_and_scales_match_reference(strategy, nv, na):
+    """Bridge only on some layers, different a2v / v2a strengths, more video than audio layers."""
+    import types
+
+    cfg = dict(O.TINY_CFG, visual_layers=nv, audio_layers=na, interaction_strategy=strategy, grid_size=(2, 2, 3),
+               audio_len=9, visual_dim=128, visual_heads=1, visual_ffn=128, audio_dim=128, audio_ffn=128, text_len=4)
+    Pv, Pa, Pb, inp = O.make_case(cfg, 5)
+    R = ref_loader.load()
+    DiTBlock = R.wan_video_dit.DiTBlock
+    vis, aud = torch.nn.Module(), torch.nn.Module()
+    vis.blocks = torch.nn.ModuleList([DiTBlock(False, 128, 1, 128, 1e-6) for _ in range(nv)])
+    aud.blocks = torch.nn.ModuleList([DiTBlock(False, 128, 1, 128, 1e-6) for _ in range(na)])
+    bridge = R.interactionv2.DualTowerConditionalBridge(visual_layers=nv, audio_layers=na, visual_hidden_dim=128,
+                                                        audio_hidden_dim=128, audio_fps=50.0, head_dim=128,
+                                                        interaction_strategy=strategy, apply_cross_rope=True)
+    vis.load_state_dict(Pv, strict=True)
+    aud.load_state_dict(Pa, strict=True)
+    bridge.load_state_dict(Pb, strict=True)
+    pipe = types.SimpleNamespace(audio_dit=aud, dual_tower_bridge=bridge)
+    with torch.no_grad():
+        rv, ra = R.forward_dual_tower_dit(
+            pipe, visual_dit=vis, visual_x=inp["visual_x"], audio_x=inp["audio_x"],
+            visual_context=inp["visual_context"], audio_context=inp["audio_context"], visual_t_mod=inp["visual_t_mod"],
+            audio_t_mod=inp["audio_t_mod"], visual_freqs=inp["visual_freqs"], audio_freqs=inp["audio_freqs"],
+            grid_size=cfg["grid_size"], video_fps=24.0, condition_scale=0.7)
+    fv, fa = O.forward_dual_tower_dit(Pv, Pa, Pb, cfg, inp["visual_x"], inp["audio_x"], inp["visual_context"],
+                                      inp["audio_context"], inp["visual_t_mod"], inp["audio_t_mod"], inp["visual_freqs"],
+                                      inp["audio_freqs"], cfg["grid_size"], 24.0, condition_scale=0.7)
+    assert (fv - rv).abs().max() <= 5e-5 * max(rv.abs().max().item(), 1.0)
+    assert (fa - ra).abs().max() <= 5e-5 * max(ra.abs().max().item(), 1.0)
+
+
+def test_sp_split_dim0_and_gather_match_reference():
+    R = ref_loader.load()
+    x = torch.arange(11 * 1 * 4, dtype=torch.float32).reshape(11, 1, 4)
+    for sp in (2, 3, 4, 8, 16):
+        chunks = []
+        for r in range(sp):
+            ref, chunk_len, pad_len, total = R.functional._sp_split_tensor_dim_0(x, sp_size=sp, sp_rank=r)
+            got, cl, pl, tt = O.sp_split(x, sp, r, dim=0)
+            assert torch.equal(got, ref) and (cl, pl, tt) == (chunk_len, pad_len, total)
+            chunks.append(got)
+        assert torch.equal(O.sp_gather(chunks, pl, dim=0), x)
