@@ -14,7 +14,7 @@ from . import _lib, cp, ops, rope  # noqa: F401
 from ._lib import MovaB200Error  # noqa: F401
 from .modules import (AttentionModule, ConditionalCrossAttention, ConditionalCrossAttentionBlock,  # noqa: F401
                       CrossAttention, CrossModalInteractionController, DiTBlock, DualTowerConditionalBridge,
-                      GateModule, RotaryEmbedding, SelfAttention)
+                      GateModule, RotaryEmbedding, SelfAttention, USPAttention)
 from .pipeline import CPRuntime, forward_dual_tower_dit, install  # noqa: F401
 
 __version__ = "0.1.0"

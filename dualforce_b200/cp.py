@@ -152,3 +152,35 @@ def all_gather_stack(x: torch.Tensor, cp: int, group: Optional[dist.ProcessGroup
     flat = torch.empty((cp * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     dist.all_gather_into_tensor(flat, x, group=group)  # concatenated along dim 0 (the form every backend accepts)
     return flat.view((cp,) + tuple(x.shape))
+
+
+def ulysses_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, attn_fn,
+                      group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Generic head <-> sequence redistribution around a local attention call, for callers that hold sequence shards
+    ``[B, S/P, H*D]`` and want the reference's ``USPAttention.forward`` contract (wan_video_dit.py:203-208: yunchang
+    LongContextAttention = all-to-all in, attention over H/P heads and the full sequence, all-to-all out).  Equal
+    shard lengths on every rank are required here (the zero-copy path in pipeline.py handles ragged video chunks).
+    ``attn_fn(q, k, v, heads)`` works on flat ``[B, S, heads*D]`` tensors."""
+    P = dist.get_world_size(group) if dist.is_initialized() else 1
+    if P == 1:
+        return attn_fn(q, k, v, num_heads)
+    B, Sl, HD = q.shape
+    if num_heads % P:
+        raise ValueError(f"{num_heads} heads cannot be split over {P} ranks")
+    D = HD // num_heads
+    Hc = num_heads // P
+
+    def scatter(t: torch.Tensor) -> torch.Tensor:
+        # [B, Sl, P, Hc*D] -> [P, B, Sl, Hc*D] (destination-rank-major) -> exchange -> [P(src), B, Sl, Hc*D]
+        send = t.reshape(B, t.shape[1], P, Hc * D).permute(2, 0, 1, 3).contiguous()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        # source rank r holds tokens [r*Sl, (r+1)*Sl): concatenate along the sequence
+        return recv.permute(1, 0, 2, 3).reshape(B, P * t.shape[1], Hc * D)
+
+    o = attn_fn(scatter(q), scatter(k), scatter(v), Hc)  # [B, S, Hc*D]
+    send = o.reshape(B, P, Sl, Hc * D).permute(1, 0, 2, 3).contiguous()  # [P(dst: its tokens), B, Sl, Hc*D]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    # recv[src] = this rank's tokens, heads of rank src -> [B, Sl, P*Hc*D]
+    return recv.permute(1, 2, 0, 3).reshape(B, Sl, HD)

@@ -27,7 +27,7 @@ from torch.nn import RMSNorm
 from . import ops, rope
 
 __all__ = [
-    "AttentionModule", "SelfAttention", "CrossAttention", "GateModule", "DiTBlock", "ConditionalCrossAttention",
+    "AttentionModule", "USPAttention", "SelfAttention", "CrossAttention", "GateModule", "DiTBlock", "ConditionalCrossAttention",
     "ConditionalCrossAttentionBlock", "CrossModalInteractionController", "RotaryEmbedding",
     "DualTowerConditionalBridge",
 ]
@@ -75,6 +75,26 @@ class AttentionModule(nn.Module):
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
         return ops.attention(q, k, v, self.num_heads)
+
+
+class USPAttention(nn.Module):
+    """wan_video_dit.py:192-208 -- the context-parallel attention processor ``MOVA.replace_attention`` installs:
+    ``forward(q, k, v)`` on sequence shards ``[B, S/P, H*D]``, Ulysses head <-> sequence all-to-all over ``group``
+    (default: the world group) around the sm_100a attention kernel.  ``attn_type`` is accepted for signature
+    compatibility and ignored (there is one kernel).  ``dualforce_b200.install`` does not need this class -- its
+    ``forward_dual_tower_dit`` shards only the video tower and exchanges without pack copies -- it exists for callers
+    that keep the reference loop and swap processors one by one."""
+
+    def __init__(self, num_heads: int, attn_type=None, group=None):
+        super().__init__()
+        self.num_heads = num_heads
+        self.attn_type = attn_type
+        self.group = group
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+        from . import cp
+
+        return cp.ulysses_attention(q, k, v, self.num_heads, ops.attention, self.group)
 
 
 class SelfAttention(nn.Module):

@@ -14,7 +14,6 @@ import types
 from typing import Optional, Sequence, Tuple
 
 import torch
-import torch.distributed as dist
 
 from . import cp as cpmod
 from . import ops, rope

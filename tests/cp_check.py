@@ -61,6 +61,18 @@ def run_check(rank: int, world: int, cfg=None, seed: int = 77):
                                          cfg["grid_size"], cfg["video_fps"])
     assert_close(fv, sv.float().cpu(), "cp vs single-GPU visual", ratio=2e-2, fro=6e-3)
     assert_close(fa, sa.float().cpu(), "cp vs single-GPU audio", ratio=2e-2, fro=6e-3)
+    # the attention-processor level drop-in (reference USPAttention contract: sequence shards in and out)
+    import dualforce_b200 as B
+
+    H = max(world, 2) if (max(world, 2) % world == 0) else world
+    S = 64 * world
+    g = torch.Generator().manual_seed(5)
+    q, k, v = (torch.randn(1, S, H * 128, generator=g).to(torch.bfloat16) for _ in range(3))
+    ref = O.attention(q.float(), k.float(), v.float(), H)
+    sl = S // world
+    sh = slice(rank * sl, (rank + 1) * sl)
+    out = B.USPAttention(H)(q[:, sh].cuda().contiguous(), k[:, sh].cuda().contiguous(), v[:, sh].cuda().contiguous())
+    assert_close(out, ref[:, sh], f"USPAttention world {world}", ratio=1e-2, fro=6e-3)
     return mv, ma
 
 

@@ -103,3 +103,32 @@ def test_plan_indices_are_permutations():
     assert cp.seq_chunks(11, 2) == [(0, 6), (6, 11)]
     with pytest.raises(ValueError):
         cp.seq_chunks(3, 8)
+
+
+def _usp_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dualforce_b200 import cp
+
+        torch.manual_seed(1)
+        H, D, S, Skv, B = 4, 16, 10, 6, 2
+        q, k, v = torch.randn(B, S, H * D), torch.randn(B, Skv, H * D), torch.randn(B, Skv, H * D)
+        ref = O.attention(q, k, v, H)
+        sl, kl = S // world, Skv // world
+        out = cp.ulysses_attention(q[:, rank * sl:(rank + 1) * sl].contiguous(), k[:, rank * kl:(rank + 1) * kl].contiguous(),
+                                   v[:, rank * kl:(rank + 1) * kl].contiguous(), H,
+                                   lambda a, b, c, h: O.attention(a, b, c, h))
+        results[rank] = (out - ref[:, rank * sl:(rank + 1) * sl]).abs().max().item()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_usp_attention_processor_world2():
+    """The USPAttention drop-in (reference contract: sequence shards in, sequence shards out) with the kernel replaced
+    by the oracle: head <-> sequence all-to-all and its inverse."""
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_usp_worker, args=(2, _free_port(), results), nprocs=2, join=True)
+    assert len(results) == 2 and all(e < 1e-5 for e in results.values()), dict(results)

@@ -3,8 +3,6 @@ import types
 
 import torch
 
-import mova_oracle as O
-
 
 def bf16_round(d):
     """Weights / inputs as the CUDA path sees them (bf16), handed to the fp32 oracle as exact fp32 values."""
