@@ -30,9 +30,7 @@
 // This kernel: 1271-1279 TFLOP/s at S = 43120, 40 heads.
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "host_utils.h"
-#include "../../include/mova_b200.h"
+#include "attn_common.cuh"
 
 namespace mv {
 
@@ -58,36 +56,6 @@ constexpr uint32_t AT_TMEM_S = 0;    // + 128 * tile
 constexpr uint32_t AT_TMEM_O = 256;  // + 128 * tile
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 constexpr int AT_DEFAULT_EMU = 4;
-
-struct AttnParams {
-  int Sq, Skv, H;
-  float scale;       // softmax scale
-  float scale_log2;  // scale * log2(e)
-  float* lse;        // [B, H, Sq] or null
-  unsigned long long* trace;  // diagnostics (MOVA_ATTN_TRACE): 3 regions of 4096 (clock << 8 | event) records
-};
-
-__device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
-__device__ __forceinline__ void setmaxnreg_dec_88() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;"); }
-
-// 2^x for a pair of scores on the FMA/ALU pipes instead of the 16-lane/clk MUFU unit (which at head_dim 128 is as
-// busy as the tensor cores): round x to the nearest integer n with the 1.5*2^23 trick, evaluate a degree-3 minimax
-// polynomial of 2^r on r = x - n in [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P) with
-// packed f32x2 instructions, then add n to the exponent field.
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 magic = make_float2(12582912.0f, 12582912.0f);
-  const float2 t = __fadd2_rn(x, magic);
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 r = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
-  float2 p = __ffma2_rn(r, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
-  p = __ffma2_rn(p, r, make_float2(0.6932609677f, 0.6932609677f));
-  p = __ffma2_rn(p, r, make_float2(0.9999280572f, 0.9999280572f));
-  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
-  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
-  return p;
-}
 
 // EMU: how many of every 16 score pairs take the polynomial path (0 = all MUFU, 8 = half and half)
 template <int EMU, bool TRACE>
@@ -465,6 +433,12 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
   p.lse = lse;
 
   debug_attach();
+  // MOVA_ATTN_VARIANT=v6 selects the experimental event-driven kernel of attn_v6.cu (see its header)
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("MOVA_ATTN_VARIANT");
+    variant = (e != nullptr && e[0] == 'v' && e[1] == '6') ? 6 : 3;
+  }
   // share of exponentials evaluated by polynomial (in 16ths of the pairs); MOVA_ATTN_EMU overrides for tuning
   static int emu = -1;
   if (emu < 0) {
@@ -494,6 +468,7 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
     }
     return 0;
   }
+  if (variant == 6) return launch_attn_v6(grid, st, tmQ, tmK, tmV, tmO, p, emu);
   switch (emu) {
     case 0: return launch_attn<0, false>(grid, st, tmQ, tmK, tmV, tmO, p);
     case 2: return launch_attn<2, false>(grid, st, tmQ, tmK, tmV, tmO, p);

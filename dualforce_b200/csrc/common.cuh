@@ -93,6 +93,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return done != 0;
 }
 
+// non-blocking probe (try_wait may park the thread for a hardware-defined time; a polling loop must not)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 #ifndef MV_MBAR_TIMEOUT_CYCLES
 #define MV_MBAR_TIMEOUT_CYCLES (6000000000LL)  // ~3-4 s of SM clock: a stuck pipeline traps, never hangs
 #endif
