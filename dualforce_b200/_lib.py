@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmova_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/mova_b200.h one to one
 SIGNATURES = {
@@ -50,6 +50,13 @@ SIGNATURES = {
          c_void_p],
     ),
     "mova_b200_add_to_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mova_b200_patchify": (
+        c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "mova_b200_unpatchify": (
+        c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mova_b200_sinusoidal": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "mova_b200_gemv_f32": (
+        c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 EPI_BIAS, EPI_GELU_TANH, EPI_RESIDUAL = 0, 1, 2

@@ -155,11 +155,25 @@ class CrossAttention(nn.Module):
         self._kv = _Packed()
 
     def kv(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """k = RMSNorm(Linear(y)), v = Linear(y) of the text context.  The prompt embedding is constant over the
+        denoising schedule, so for a context flagged static by ``step.embed_text`` the result is memoised (the
+        reference recomputes it in every layer of every forward, wan_video_dit.py:218-223)."""
         d = self.dim
         w, b = self._kv.get([self.k, self.v])
+        static = getattr(y, "_mova_b200_static", False)
+        if static:
+            key = (y.data_ptr(), tuple(y.shape), y._version, w.data_ptr())
+            memo = self.__dict__.setdefault("_kv_memo", {})
+            hit = memo.get(key)
+            if hit is not None:
+                return hit[1]
         kv = ops.linear(y, w, b)
         k, v = kv[..., :d], kv[..., d:]
         ops.rmsnorm_rope_(k, self.norm_k.weight, self.norm_k.eps)
+        if static:
+            while len(memo) >= 4:  # positive + negative prompt, with slack
+                memo.pop(next(iter(memo)))
+            memo[key] = (y, (k, v))  # y kept alive so its storage is not recycled under the key
         return k, v
 
     def attend(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -13,7 +13,8 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_GELU_TANH, EPI_RESIDUAL, ROPE_HALF, ROPE_INTERLEAVED, ROPE_NONE  # noqa: F401
 
 __all__ = [
-    "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32",
+    "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32", "patchify", "unpatchify",
+    "sinusoidal_embedding", "gemv_f32",
     "EPI_BIAS", "EPI_GELU_TANH", "EPI_RESIDUAL", "ROPE_NONE", "ROPE_INTERLEAVED", "ROPE_HALF",
 ]
 
@@ -260,3 +261,93 @@ def add_to_f32(a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tenso
     rc = _lib.load().mova_b200_add_to_f32(a.data_ptr(), bptr, out.data_ptr(), a.numel(), _stream())
     _lib.check(rc, "mova_b200_add_to_f32")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the step either side of the dual-tower forward (MOVA.inference_single_step, pipeline_mova.py:500-609)
+# ----------------------------------------------------------------------------------------------------------------
+def patchify(x: torch.Tensor, patch_size, *, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """im2col of the stride == kernel patch embedding: ``x [C, F, H, W]`` (or ``[C, F]`` for the audio Conv1d),
+    fp32 or bf16 -> bf16 ``[L, C*pt*ph*pw]`` with tokens in (f, h, w) order and columns in the order of
+    ``conv.weight.view(dim, -1)`` (wan_video_dit.py:399-409; wan_audio_dit.py:180-189).  The bf16 cast of
+    pipeline_mova.py:556-557 is fused."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise _lib.MovaB200Error(f"patchify: x must be fp32 or bf16, got {x.dtype}")
+    _need(x, x.dtype, "x")
+    if x.dim() == 2:
+        x = x[:, :, None, None]
+    if x.dim() != 4 or not x.is_contiguous():
+        raise _lib.MovaB200Error(f"patchify: x must be a contiguous [C, F, H, W] (or [C, F]) tensor, got {tuple(x.shape)}")
+    p = tuple(int(v) for v in patch_size) + (1, 1)
+    pt, ph, pw = p[0], p[1], p[2]
+    C, F, H, W = x.shape
+    if F % pt or H % ph or W % pw:
+        raise _lib.MovaB200Error(f"patchify: latent {F}x{H}x{W} is not a multiple of the patch {pt}x{ph}x{pw}")
+    L, K = (F // pt) * (H // ph) * (W // pw), C * pt * ph * pw
+    if out is None:
+        out = torch.empty(L, K, dtype=torch.bfloat16, device=x.device)
+    _need(out, torch.bfloat16, "out")
+    Lo, Ko, ldo = _rows2d(out, "out")
+    if (Lo, Ko) != (L, K):
+        raise _lib.MovaB200Error(f"patchify: out is {Lo}x{Ko}, expected {L}x{K}")
+    rc = _lib.load().mova_b200_patchify(x.data_ptr(), int(x.dtype == torch.float32), C, F, H, W, pt, ph, pw,
+                                        out.data_ptr(), ldo, _stream())
+    _lib.check(rc, "mova_b200_patchify")
+    return out
+
+
+def unpatchify(x: torch.Tensor, grid_size, patch_size, out_channels: int) -> torch.Tensor:
+    """``'(f h w) (x y z c) -> c (f x) (h y) (w z)'`` (wan_video_dit.py:411-416; wan_audio_dit.py:191-195 with
+    y = z = 1): ``x [L, pt*ph*pw*C]`` bf16 -> ``[C, F*pt, H*ph, W*pw]`` bf16 (``[C, F*pt]`` for a 1-D grid)."""
+    _need(x, torch.bfloat16, "x")
+    L, cols, ldi = _rows2d(x, "x")
+    g = tuple(int(v) for v in grid_size)
+    one_d = len(g) == 1
+    g = g + (1, 1)
+    p = tuple(int(v) for v in patch_size) + (1, 1)
+    Fp, Hp, Wp = g[0], g[1], g[2]
+    pt, ph, pw = p[0], p[1], p[2]
+    if L != Fp * Hp * Wp or cols != pt * ph * pw * out_channels:
+        raise _lib.MovaB200Error(f"unpatchify: x is {L}x{cols}, grid {g[:3]} patch {p[:3]} channels {out_channels}")
+    out = torch.empty(out_channels, Fp * pt, Hp * ph, Wp * pw, dtype=torch.bfloat16, device=x.device)
+    rc = _lib.load().mova_b200_unpatchify(x.data_ptr(), ldi, out.data_ptr(), out_channels, Fp, Hp, Wp, pt, ph, pw,
+                                          _stream())
+    _lib.check(rc, "mova_b200_unpatchify")
+    return out.reshape(out_channels, Fp * pt) if one_d else out
+
+
+def sinusoidal_embedding(dim: int, timestep: torch.Tensor) -> torch.Tensor:
+    """sinusoidal_embedding_1d (wan_video_dit.py:99-103) for one timestep: fp32 ``[dim]``, fp64 math on the device;
+    ``timestep`` is a one-element fp32 CUDA tensor and is not synchronised with the host."""
+    _need(timestep, torch.float32, "timestep")
+    if timestep.numel() != 1:
+        raise _lib.MovaB200Error(f"sinusoidal_embedding: one timestep per call (MOVA runs B = 1), got {tuple(timestep.shape)}")
+    out = torch.empty(dim, dtype=torch.float32, device=timestep.device)
+    rc = _lib.load().mova_b200_sinusoidal(timestep.data_ptr(), out.data_ptr(), int(dim), _stream())
+    _lib.check(rc, "mova_b200_sinusoidal")
+    return out
+
+
+def gemv_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, pre_silu: bool = False,
+             post_silu: bool = False, want_bf16: bool = False):
+    """``post(W pre(x) + b)`` for one fp32 activation vector and bf16 weights, fp32 accumulation and result: the
+    M = 1 time_embedding / time_projection MLPs (wan_video_dit.py:374-380) as the reference evaluates them under
+    autocast(float32) (pipeline_mova.py:544-549).  Returns fp32 ``[N]`` (and its bf16 rounding when ``want_bf16``)."""
+    _need(x, torch.float32, "x")
+    _need(weight, torch.bfloat16, "weight")
+    N, K, ldw = _rows2d(weight, "weight")
+    if x.numel() != K or not x.is_contiguous():
+        raise _lib.MovaB200Error(f"gemv_f32: x must be a contiguous fp32 vector of K={K} elements, got {tuple(x.shape)}")
+    bptr = None
+    if bias is not None:
+        _need(bias, torch.bfloat16, "bias")
+        if bias.numel() != N or not bias.is_contiguous():
+            raise _lib.MovaB200Error("gemv_f32: bias must be a contiguous bf16 vector of N elements")
+        bptr = bias.data_ptr()
+    y = torch.empty(N, dtype=torch.float32, device=x.device)
+    yb = torch.empty(N, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    rc = _lib.load().mova_b200_gemv_f32(x.data_ptr(), weight.data_ptr(), ldw, bptr, y.data_ptr(),
+                                        yb.data_ptr() if yb is not None else None, N, K, int(pre_silu), int(post_silu),
+                                        _stream())
+    _lib.check(rc, "mova_b200_gemv_f32")
+    return (y, yb) if want_bf16 else y

@@ -172,9 +172,12 @@ def _forward_eager(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tens
                            audio_t_mod: Optional[torch.Tensor], visual_freqs: torch.Tensor, audio_freqs: torch.Tensor,
                            grid_size: Tuple[int, int, int], video_fps: float, condition_scale: Optional[float] = 1.0,
                            a2v_condition_scale: Optional[float] = None, v2a_condition_scale: Optional[float] = None,
-                           cp_mesh=None):
+                           cp_mesh=None, _gather: bool = True):
     """Same contract as pipeline_mova.py:612-711: returns full-length ``(visual_x, audio_x)`` hidden states.
-    ``self`` only needs ``audio_dit`` and ``dual_tower_bridge`` attributes (a ``MOVA`` pipeline after ``install``)."""
+    ``self`` only needs ``audio_dit`` and ``dual_tower_bridge`` attributes (a ``MOVA`` pipeline after ``install``).
+
+    ``_gather=False`` (context parallel only, used by ``step.inference_single_step``) skips the final all-gather and
+    returns ``(visual_x_local, audio_x, rows_per_rank, group)`` so the head can run on the local chunk."""
     audio_dit, bridge = self.audio_dit, self.dual_tower_bridge
     _check_modules(visual_dit, audio_dit, bridge)
     if visual_x.shape[0] != 1 and cp_mesh is not None:
@@ -231,6 +234,8 @@ def _forward_eager(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tens
         audio_x = audio_dit.blocks[i](audio_x, audio_context, audio_t_mod, a_tab)  # replicated
     for i in range(min_layers, visual_layers):
         x_loc = _video_block_cp(visual_dit.blocks[i], x_loc, visual_context, visual_t_mod, v_tab_loc, rt, rows)
+    if not _gather:
+        return x_loc, audio_x, rows, rt.group
     visual_full = cpmod.all_gather_cat(x_loc, rows, rt.group, dim=1)
     return visual_full, audio_x
 
@@ -340,4 +345,13 @@ def install(pipe, cuda_graph: bool = False) -> int:
             pipe.dual_tower_bridge.video_to_audio_conditioners)
     pipe.forward_dual_tower_dit = types.MethodType(forward_dual_tower_dit, pipe)
     pipe.mova_b200_cuda_graph = bool(cuda_graph)
+    # the step around the path (pipeline_mova.py:500-609): heads share the reference parameters
+    from . import step
+
+    for name in ("video_dit", "video_dit_2", "audio_dit"):
+        model = getattr(pipe, name, None)
+        if model is not None and hasattr(model, "head") and not isinstance(model.head, step.Head):
+            model.head = step.Head.from_reference(model.head)
+            count += 1
+    step.bind(pipe)
     return count

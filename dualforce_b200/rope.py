@@ -94,10 +94,11 @@ def as_tables(freqs) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
     return tables_from_complex(freqs)
 
 
-def precompute_freqs_cis(dim: int, end: int = 1024, theta: float = 10000.0) -> torch.Tensor:
-    """1-D complex table, same formula as wan_video_dit.py:115-121 (float64 angles)."""
+def precompute_freqs_cis(dim: int, end: int = 1024, theta: float = 10000.0, s: float = 1.0) -> torch.Tensor:
+    """1-D complex table, same formula as wan_video_dit.py:115-121 (float64 angles); ``s`` scales the positions
+    (wan_audio_dit.py:53-60)."""
     freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[: (dim // 2)].double() / dim))
-    freqs = torch.outer(torch.arange(end, dtype=torch.float64), freqs)
+    freqs = torch.outer(torch.arange(end, dtype=torch.float64) * s, freqs)
     return torch.polar(torch.ones_like(freqs), freqs)
 
 
@@ -110,6 +111,16 @@ def precompute_freqs_cis_3d(dim: int, end: int = 1024, theta: float = 10000.0):
 def precompute_freqs_cis_1d(dim: int, end: int = 16384, theta: float = 10000.0):
     """Audio tower: one 1-D table over all 64 pairs, chunked in 3 (wan_audio_dit.py:48-50)."""
     return precompute_freqs_cis(dim, end, theta).chunk(3, dim=-1)
+
+
+def legacy_precompute_freqs_cis_1d(dim: int, end: int = 16384, theta: float = 10000.0, base_tps: float = 4.0,
+                                   target_tps: float = 44100 / 2048):
+    """``vae_type="oobleck"`` tables (wan_audio_dit.py:37-45): rescaled positions on the first 22 pairs, identity
+    rotation on the other 2 x 21 (MOVA ships ``vae_type="dac"``; kept for constructor parity)."""
+    s = float(base_tps) / float(target_tps)
+    f = precompute_freqs_cis(dim - 2 * (dim // 3), end, theta, s)
+    ones = torch.ones_like(precompute_freqs_cis(dim // 3, end, theta, s))
+    return f, ones, ones
 
 
 def video_freqs(tables, grid_size, device) -> torch.Tensor:

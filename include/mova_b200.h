@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOVA_B200_ABI_VERSION 1
+#define MOVA_B200_ABI_VERSION 2
 
 /* epilogues of mova_b200_linear */
 #define MOVA_EPI_BIAS 0      /* C = A W^T + b                          nn.Linear                          */
@@ -125,6 +125,41 @@ int mova_b200_rmsnorm_rope_seg(void* x, int64_t ldx, int seg_len, int64_t seg_st
 
 /* out[i] = float(a[i]) + float(b[i]), bf16 inputs (b may be NULL): modulation + t_mod, wan_video_dit.py:279-280 */
 int mova_b200_add_to_f32(const void* a, const void* b, float* out, int64_t n, void* stream);
+
+/* ---- the step either side of the dual-tower forward: MOVA.inference_single_step, pipeline_mova.py:500-609 ---- */
+
+/*
+ * im2col of the patch embedding (nn.Conv3d / nn.Conv1d with stride == kernel: wan_video_dit.py:367-368,399-409;
+ * wan_audio_dit.py:143-145,180-189) so the convolution runs as one mova_b200_linear call on
+ * weight.view(dim, C*pt*ph*pw).  Also replaces the `.to(model_dtype)` cast at pipeline_mova.py:556-557.
+ *   x:   [C, F, H, W] contiguous, fp32 (x_is_f32 != 0) or bf16     (audio: H = W = 1, patch (p, 1, 1))
+ *   out: bf16 [L, ldo], L = (F/pt)(H/ph)(W/pw) tokens in (f, h, w) order, column ((c*pt + dt)*ph + dh)*pw + dw
+ */
+int mova_b200_patchify(const void* x, int x_is_f32, int C, int F, int H, int W, int pt, int ph, int pw, void* out,
+                       int64_t ldo, void* stream);
+
+/*
+ * WanModel.unpatchify / WanAudioModel.unpatchify (wan_video_dit.py:411-416; wan_audio_dit.py:191-195):
+ *   in:  bf16 [L, ldi] head output, column ((x*ph + y)*pw + z)*Cout + c, tokens in (f, h, w) order
+ *   out: bf16 [Cout, Fp*pt, Hp*ph, Wp*pw] contiguous
+ */
+int mova_b200_unpatchify(const void* in, int64_t ldi, void* out, int Cout, int Fp, int Hp, int Wp, int pt, int ph,
+                         int pw, void* stream);
+
+/*
+ * sinusoidal_embedding_1d (wan_video_dit.py:99-103), fp64 math like the reference:
+ *   out[i] = cos(t[0] * 10000^(-i/(dim/2))), out[dim/2 + i] = sin(...), i < dim/2;  t: one fp32 value on the device
+ */
+int mova_b200_sinusoidal(const float* t, float* out, int dim, void* stream);
+
+/*
+ * One row of an nn.Linear in fp32: y[n] = post(sum_k pre(x[k]) W[n,k] + bias[n]); pre/post: 0 = identity, 1 = SiLU.
+ * The time_embedding / time_projection MLPs (wan_video_dit.py:374-380) which the reference evaluates under
+ * autocast(float32) (pipeline_mova.py:544-549): fp32 activations, bf16-valued weights.
+ *   x fp32 [K], W bf16 [N, ldw], bias bf16 [N] or NULL, y fp32 [N], y_bf16 bf16 [N] or NULL (rounded copy)
+ */
+int mova_b200_gemv_f32(const float* x, const void* W, int64_t ldw, const void* bias, float* y, void* y_bf16, int N,
+                       int K, int pre_act, int post_act, void* stream);
 
 #ifdef __cplusplus
 }

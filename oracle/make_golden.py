@@ -75,6 +75,68 @@ def run_reference(cfg, seed):
     return {k: v.detach().numpy() for k, v in out.items()}, O.checksum(Pv, Pa, Pb, inp), keys
 
 
+def build_reference_step(cfg, Pv, Pa, Pb):
+    """Reference WanModel / WanAudioModel / bridge holding the oracle's step-level weights, and a pipeline stand-in
+    whose two methods are the reference's own source (lifted by ref_loader)."""
+    R = ref_loader.load()
+    common = dict(text_dim=cfg["text_dim"], freq_dim=cfg["freq_dim"], eps=cfg["eps"], has_image_input=False)
+    vis = R.wan_video_dit.WanModel(dim=cfg["visual_dim"], in_dim=cfg["visual_in_dim"], ffn_dim=cfg["visual_ffn"],
+                                   out_dim=cfg["visual_out_dim"], patch_size=tuple(cfg["visual_patch"]),
+                                   num_heads=cfg["visual_heads"], num_layers=cfg["visual_layers"], **common)
+    aud = R.wan_audio_dit.WanAudioModel(dim=cfg["audio_dim"], in_dim=cfg["audio_in_dim"], ffn_dim=cfg["audio_ffn"],
+                                        out_dim=cfg["audio_out_dim"], patch_size=list(cfg["audio_patch"]),
+                                        num_heads=cfg["audio_heads"], num_layers=cfg["audio_layers"], vae_type="dac",
+                                        **common)
+    bridge = R.interactionv2.DualTowerConditionalBridge(
+        visual_layers=cfg["visual_layers"], audio_layers=cfg["audio_layers"], visual_hidden_dim=cfg["visual_dim"],
+        audio_hidden_dim=cfg["audio_dim"], audio_fps=cfg["audio_fps"], head_dim=cfg["head_dim"],
+        interaction_strategy=cfg["interaction_strategy"], apply_cross_rope=cfg["apply_cross_rope"])
+    vis.load_state_dict(Pv, strict=True)
+    aud.load_state_dict(Pa, strict=True)
+    bridge.load_state_dict(Pb, strict=True)
+    pipe = types.SimpleNamespace(audio_dit=aud, dual_tower_bridge=bridge, _pre_forward=lambda model: None)
+    pipe.forward_dual_tower_dit = types.MethodType(R.forward_dual_tower_dit, pipe)
+    pipe.inference_single_step = types.MethodType(R.inference_single_step, pipe)
+    return R, vis, aud, bridge, pipe
+
+
+@torch.no_grad()
+def run_reference_step(cfg, seed):
+    """One MOVA.inference_single_step (pipeline_mova.py:500-609) of the reference in fp32 on CPU, with the
+    intermediate embeddings the B200 step memoises."""
+    import warnings
+
+    Pv, Pa, Pb, inp = O.make_step_case(cfg, seed)
+    R, vis, aud, bridge, pipe = build_reference_step(cfg, Pv, Pa, Pb)
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # torch.autocast("cuda") without a GPU only warns and disables itself
+        v, a = pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"],
+                                          audio_latents=inp["audio_latents"], context=inp["context"],
+                                          timestep=inp["timestep"], audio_timestep=None, video_fps=cfg["video_fps"])
+    out["visual_output"], out["audio_output"] = v, a
+    e = R.wan_video_dit.sinusoidal_embedding_1d(cfg["freq_dim"], inp["timestep"])
+    out["sinusoidal"] = e
+    out["visual_t"] = vis.time_embedding(e)
+    out["visual_t_mod"] = vis.time_projection(out["visual_t"]).unflatten(1, (6, cfg["visual_dim"]))
+    out["audio_t"] = aud.time_embedding(e)
+    out["visual_context"] = vis.text_embedding(inp["context"])
+    out["audio_context"] = aud.text_embedding(inp["context"])
+    out["visual_tokens"], grid = vis.patchify(inp["visual_latents"])
+    out["audio_tokens"], agrid = aud.patchify(inp["audio_latents"], None)
+    assert tuple(grid) == tuple(cfg["grid_size"]) and tuple(agrid) == (cfg["audio_len"],)
+    hv = vis.head(out["visual_tokens"], out["visual_t"])
+    out["visual_head"] = hv
+    out["visual_unpatchify"] = vis.unpatchify(hv, grid)
+    ha = aud.head(out["audio_tokens"], out["audio_t"])
+    out["audio_unpatchify"] = aud.unpatchify(ha, agrid)
+    # the full single-tower forwards (wan_video_dit.py:418-473, wan_audio_dit.py:197-252)
+    out["video_tower_forward"] = vis(inp["visual_latents"], inp["timestep"], inp["context"])
+    out["audio_tower_forward"] = aud(inp["audio_latents"], inp["timestep"], inp["context"])
+    keys = {"wan_model": sorted(vis.state_dict().keys()), "wan_audio_model": sorted(aud.state_dict().keys())}
+    return {k: t.detach().numpy() for k, t in out.items()}, O.checksum(Pv, Pa, Pb, inp), keys
+
+
 def main():
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -82,6 +144,15 @@ def main():
         arrays, csum, keys = run_reference(cfg, seed)
         meta = dict(cfg=cfg, seed=seed, checksum=csum, torch=torch.__version__, reference_state_dict_keys=keys,
                     source="reference modules from /root/reference run in fp32 on CPU by oracle/make_golden.py")
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrays)
+        with open(os.path.join(out_dir, name + ".json"), "w") as f:
+            json.dump(meta, f, indent=1, sort_keys=True)
+        print(name, {k: v.shape for k, v in arrays.items()}, "checksum", csum)
+    for name, cfg, seed in (("tiny_step", O.TINY_STEP_CFG, 1234),):
+        arrays, csum, keys = run_reference_step(cfg, seed)
+        meta = dict(cfg=cfg, seed=seed, checksum=csum, torch=torch.__version__, reference_state_dict_keys=keys,
+                    source="reference WanModel / WanAudioModel / bridge + MOVA.inference_single_step (source lifted from "
+                           "pipeline_mova.py:500-609) run in fp32 on CPU by oracle/make_golden.py")
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **arrays)
         with open(os.path.join(out_dir, name + ".json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)

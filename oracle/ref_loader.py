@@ -31,7 +31,8 @@ _loaded = None
 
 def load():
     """Returns a namespace with the reference's wan_video_dit, wan_audio_dit, interactionv2 and functional modules
-    plus ``forward_dual_tower_dit`` lifted (source unchanged) out of pipeline_mova.py:612-711."""
+    plus ``forward_dual_tower_dit`` (pipeline_mova.py:612-711) and ``inference_single_step`` (:500-609) lifted, source
+    unchanged, out of pipeline_mova.py."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -101,27 +102,33 @@ def load():
     interactionv2 = importlib.import_module("mova.diffusion.models.interactionv2")
     functional = importlib.import_module("mova.distributed.functional")
 
-    # lift MOVA.forward_dual_tower_dit verbatim (pipeline_mova.py needs diffusers/transformers/ftfy to import)
+    # lift MOVA.forward_dual_tower_dit and MOVA.inference_single_step verbatim (pipeline_mova.py itself needs
+    # diffusers/transformers/ftfy to import)
     src_path = os.path.join(REFERENCE_ROOT, "mova", "diffusion", "pipelines", "pipeline_mova.py")
     with open(src_path) as f:
         tree = ast.parse(f.read())
-    fn_node = None
-    for node in ast.walk(tree):
-        if isinstance(node, ast.FunctionDef) and node.name == "forward_dual_tower_dit":
-            fn_node = node
-            break
-    assert fn_node is not None, "forward_dual_tower_dit not found in pipeline_mova.py"
-    fn_node.decorator_list = []
-    module = ast.Module(body=[fn_node], type_ignores=[])
-    ast.fix_missing_locations(module)
     ns = {
         "torch": torch, "Optional": Optional, "DeviceMesh": object,
+        "sinusoidal_embedding_1d": wan_video_dit.sinusoidal_embedding_1d,
         "_sp_split_tensor": functional._sp_split_tensor, "_sp_split_tensor_dim_0": functional._sp_split_tensor_dim_0,
         "_sp_all_gather_avg": functional._sp_all_gather_avg,
     }
-    exec(compile(module, src_path, "exec"), ns)
+    lifted_lines = {}
+    for name in ("forward_dual_tower_dit", "inference_single_step"):
+        fn_node = None
+        for node in ast.walk(tree):
+            if isinstance(node, ast.FunctionDef) and node.name == name:
+                fn_node = node
+                break
+        assert fn_node is not None, f"{name} not found in pipeline_mova.py"
+        fn_node.decorator_list = []
+        module = ast.Module(body=[fn_node], type_ignores=[])
+        ast.fix_missing_locations(module)
+        exec(compile(module, src_path, "exec"), ns)
+        lifted_lines[name] = (fn_node.lineno, fn_node.end_lineno)
 
     _loaded = types.SimpleNamespace(
         wan_video_dit=wan_video_dit, wan_audio_dit=wan_audio_dit, interactionv2=interactionv2, functional=functional,
-        forward_dual_tower_dit=ns["forward_dual_tower_dit"], lines=(fn_node.lineno, fn_node.end_lineno))
+        forward_dual_tower_dit=ns["forward_dual_tower_dit"], inference_single_step=ns["inference_single_step"],
+        lines=lifted_lines["forward_dual_tower_dit"], step_lines=lifted_lines["inference_single_step"])
     return _loaded

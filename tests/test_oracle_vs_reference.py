@@ -103,3 +103,20 @@ def test_sp_split_dim0_and_gather_match_reference():
             assert torch.equal(got, ref) and (cl, pl, tt) == (chunk_len, pad_len, total)
             chunks.append(got)
         assert torch.equal(O.sp_gather(chunks, pl, dim=0), x)
+
+
+@pytest.mark.parametrize("seed,grid,audio_len,timestep", [(5, (2, 3, 2), 9, 37.5), (11, (1, 2, 6), 14, 999.0)])
+def test_step_matches_reference(seed, grid, audio_len, timestep):
+    """MOVA.inference_single_step (source lifted from pipeline_mova.py:500-609) at other seeds / geometries /
+    timesteps than the committed golden."""
+    import make_golden
+
+    cfg = dict(O.TINY_STEP_CFG, grid_size=grid, audio_len=audio_len, timestep=timestep)
+    arrays, _, _ = make_golden.run_reference_step(cfg, seed)
+    Pv, Pa, Pb, inp = O.make_step_case(cfg, seed)
+    v, a = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], inp["context"],
+                                   inp["timestep"])
+    for got, key in ((v, "visual_output"), (a, "audio_output")):
+        ref = torch.from_numpy(arrays[key])
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max() <= 5e-5 * max(ref.abs().max().item(), 1.0)
