@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 FULL_360P = dict(visual_dim=5120, visual_heads=40, visual_ffn=13824, visual_layers=40, audio_dim=1536, audio_heads=12,
                  audio_ffn=8960, audio_layers=30, head_dim=128, interaction_strategy="full", apply_cross_rope=True,
                  audio_fps=50.0, grid_size=(49, 22, 40), audio_len=403, text_len=512, eps=1e-6, video_fps=24.0)
+# tower-level hyper-parameters of the MOVA-360p checkpoint around the blocks
+STEP_360P = dict(visual_in_dim=36, visual_out_dim=16, visual_patch=(1, 2, 2), audio_in_dim=128, audio_out_dim=128,
+                 audio_patch=(1,), text_dim=4096, freq_dim=256)
 METRIC = "denoise steps/sec, MOVA-360p dual-tower DiT (2 CFG forwards per step)"
 UNIT = "steps/s"
 FORWARDS_PER_STEP = 2
@@ -179,7 +182,7 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------------
-def build_model(cfg, device, seed=0):
+def build_model(cfg, device, seed=0, with_step=False):
     import torch
 
     import dualforce_b200 as B
@@ -195,6 +198,20 @@ def build_model(cfg, device, seed=0):
             aud = torch.nn.Module()
             aud.blocks = torch.nn.ModuleList([B.DiTBlock(False, cfg["audio_dim"], cfg["audio_heads"], cfg["audio_ffn"],
                                                          cfg["eps"]) for _ in range(cfg["audio_layers"])])
+            if with_step:
+                # the rest of WanModel / WanAudioModel: embeddings, patch embedding, head -- what
+                # MOVA.inference_single_step drives around the path.  Zero-layer twins donate those parameters; the
+                # block lists above stay exactly as the forward-level measurement has always built them.
+                tv = B.WanModel(dim=cfg["visual_dim"], in_dim=STEP_360P["visual_in_dim"], ffn_dim=cfg["visual_ffn"],
+                                out_dim=STEP_360P["visual_out_dim"], text_dim=STEP_360P["text_dim"],
+                                freq_dim=STEP_360P["freq_dim"], eps=cfg["eps"], patch_size=STEP_360P["visual_patch"],
+                                num_heads=cfg["visual_heads"], num_layers=0, has_image_input=False)
+                ta = B.WanAudioModel(dim=cfg["audio_dim"], in_dim=STEP_360P["audio_in_dim"], ffn_dim=cfg["audio_ffn"],
+                                     out_dim=STEP_360P["audio_out_dim"], text_dim=STEP_360P["text_dim"],
+                                     freq_dim=STEP_360P["freq_dim"], eps=cfg["eps"], patch_size=STEP_360P["audio_patch"],
+                                     num_heads=cfg["audio_heads"], num_layers=0, has_image_input=False, vae_type="dac")
+                tv.blocks, ta.blocks = vis.blocks, aud.blocks
+                vis, aud = tv, ta
             bridge = B.DualTowerConditionalBridge(
                 visual_layers=cfg["visual_layers"], audio_layers=cfg["audio_layers"], visual_hidden_dim=cfg["visual_dim"],
                 audio_hidden_dim=cfg["audio_dim"], audio_fps=cfg["audio_fps"], head_dim=cfg["head_dim"],
@@ -205,7 +222,28 @@ def build_model(cfg, device, seed=0):
 
     pipe = types.SimpleNamespace(video_dit=vis, video_dit_2=None, audio_dit=aud, dual_tower_bridge=bridge)
     pipe.forward_dual_tower_dit = types.MethodType(B.forward_dual_tower_dit, pipe)
+    if with_step:
+        pipe.inference_single_step = types.MethodType(B.inference_single_step, pipe)
     return pipe
+
+
+def host_step_inputs(cfg, seed=2):
+    """Pinned host tensors of one denoising step as MOVA.__call__ hands them to inference_single_step
+    (pipeline_mova.py:416-437): fp32 latents (16 noise + 20 condition channels), fp32 audio latents, the two T5
+    prompt embeddings [1, 512, 4096] bf16, the timestep."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    f, h, w = cfg["grid_size"]
+    pt, ph, pw = STEP_360P["visual_patch"]
+    inp = {"visual_latents": torch.randn(1, STEP_360P["visual_in_dim"], f * pt, h * ph, w * pw, generator=g).pin_memory(),
+           "audio_latents": torch.randn(1, STEP_360P["audio_in_dim"], cfg["audio_len"], generator=g).pin_memory(),
+           "timestep": torch.tensor([900.0], dtype=torch.float32).pin_memory()}
+    for name in ("pos", "neg"):
+        c = torch.randn(1, cfg["text_len"], STEP_360P["text_dim"], generator=g)
+        c[:, 64:] = 0  # zero-padded T5 tokens (pipeline_mova.py:309-312)
+        inp[f"context_{name}"] = c.to(torch.bfloat16).pin_memory()
+    return inp
 
 
 def host_inputs(cfg, seed=1):
@@ -271,7 +309,15 @@ def run_b200_arm(args):
         cfg["grid_size"] = ((args.frames - 1) // 4 + 1, 22, 40)
     full = (cfg == FULL_360P)
 
-    pipe = build_model(cfg, device)
+    step_api_error = None
+    want_step_api = os.environ.get("MOVA_BENCH_STEP_API", "1") != "0"
+    try:
+        pipe = build_model(cfg, device, with_step=want_step_api)
+    except Exception as exc:  # the forward-level measurement must not depend on the step wrapper
+        if not want_step_api:
+            raise
+        step_api_error = f"build: {exc!r}"[:300]
+        pipe = build_model(cfg, device, with_step=False)
     # eager launches by default: graph replay measured within 0.5 % of eager at 1 and 8 GPUs (the GPU, not the host,
     # is the bottleneck), and NCCL communicators captured into a graph can stall process-group teardown
     use_graph = bool(args.cuda_graph) if args.cuda_graph is not None else False
@@ -394,6 +440,57 @@ def run_b200_arm(args):
     h2d = sum(nbytes(v) for v in host.values())
     d2h = sum(nbytes(t) for pair in out_host for t in pair)
 
+    # ... and through the step-level public API, the call MOVA.__call__ makes (pipeline_mova.py:429-456):
+    # latents / prompt embeddings / timestep from pinned host memory in, denoised latents out.  Measured last and
+    # guarded: a failure here is reported in the line and leaves every number above untouched.
+    e2e_step = None
+    if want_step_api and step_api_error is None:
+        try:
+            host_s = host_step_inputs(cfg)
+            out_host_s = None
+            # a new timestep every step, like the scheduler loop (one pinned scalar each: an async copy never reads a
+            # buffer the host has since rewritten)
+            ts_host = [torch.tensor([900.0 - 18.0 * i], dtype=torch.float32).pin_memory() for i in range(args.steps + 4)]
+            ts_next = [0]
+
+            def step_e2e_api():
+                nonlocal out_host_s
+                host_s["timestep"] = ts_host[ts_next[0] % len(ts_host)]
+                ts_next[0] += 1
+                d = {k: v.to(device, non_blocking=True) for k, v in host_s.items() if not k.startswith("context_")}
+                outs = []
+                for which in ("pos", "neg"):
+                    outs.append(pipe.inference_single_step(
+                        visual_dit=pipe.video_dit, visual_latents=d["visual_latents"], audio_latents=d["audio_latents"],
+                        context=ctx_dev[which], timestep=d["timestep"], audio_timestep=None, video_fps=cfg["video_fps"],
+                        cp_mesh=cp_mesh))
+                if out_host_s is None:
+                    out_host_s = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in pair] for pair in outs]
+                if rank == 0:
+                    for pair, hpair in zip(outs, out_host_s):
+                        for t, ht in zip(pair, hpair):
+                            ht.copy_(t, non_blocking=True)
+                return outs
+
+            # the two prompt embeddings are uploaded once per video, as in MOVA.__call__ (:404-405), not once per step
+            ctx_dev = {w_: host_s[f"context_{w_}"].to(device) for w_ in ("pos", "neg")}
+            launches1 = _lib.LAUNCHES
+            step_e2e_api()  # first step: fills the prompt memos (text embedding, per-layer text k / v)
+            step_e2e_api()
+            launches_step_api = (_lib.LAUNCHES - launches1)
+            step_e2e_api()
+            launches_step_api = _lib.LAUNCHES - launches1 - launches_step_api  # launches of one steady-state step
+            ms_api = timed(step_e2e_api, args.steps)
+            per_step_in = sum(nbytes(host_s[k]) for k in ("visual_latents", "audio_latents", "timestep"))
+            e2e_step = {"value": 1e3 / (ms_api / args.steps), "unit": UNIT, "h2d_bytes_per_step": per_step_in,
+                        "d2h_bytes_per_step": sum(nbytes(t) for pair in out_host_s for t in pair),
+                        "ms_per_step": ms_api / args.steps, "gpu_launches_per_step": launches_step_api,
+                        "api": "2 x pipe.inference_single_step (pipeline_mova.py:500-609 drop-in): fp32 latents + "
+                               "timestep from pinned host memory in, bf16 denoised latents out; prompt embeddings "
+                               "resident (uploaded once per video)"}
+        except Exception as exc:
+            step_api_error = repr(exc)[:300]
+
     if rank == 0:
         ms_step = ms_total / args.steps
         value = 1e3 / ms_step
@@ -414,10 +511,18 @@ def run_b200_arm(args):
             "model_flops_frac_of_sustained_peak": flops_step / (ms_step * 1e-3) / 1e12 / (peaks["sustained"] * world),
             "clocks": clocks,
             "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "api": "2 x pipe.forward_dual_tower_dit (pipeline_mova.py:612-711 drop-in): token-level hidden "
+                           "states, contexts, t_mod and RoPE tables from pinned host memory in, hidden states out"},
             "gpu_launches": launches,
             "roofline": roofline,
         }
+        if e2e_step is not None:
+            # the headline end-to-end number is the call a user of the reference makes per scheduler iteration
+            line["e2e_forward_api"] = line["e2e"]
+            line["e2e"] = e2e_step
+        if step_api_error is not None:
+            line["e2e_step_api_error"] = step_api_error
         if world == 1 and not args.no_cpu_baseline:
             run, scale, cores = cpu_sample_runner()
             run()  # warm-up (thread pool, allocator)
@@ -425,7 +530,15 @@ def run_b200_arm(args):
             line["cpu_baseline"] = {"value": 1.0 / (sec * scale), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": CPU_SAMPLE_TEXT, "sample_seconds": sec}
         emit(line)
+    if world == 1 and step_api_error is not None:  # a failed launch leaves a sticky context error: skip teardown
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     if world > 1:
+        if step_api_error is not None:  # the device / communicator may be unusable: the line is out, leave
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.barrier()
         torch.cuda.synchronize()
         if use_graph:

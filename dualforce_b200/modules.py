@@ -10,7 +10,7 @@ so they load the reference's checkpoints and drop into ``MOVA`` (``dualforce_b20
 ``nn.LayerNorm`` / ``nn.RMSNorm`` objects are kept only as parameter containers; every ``forward`` here runs the
 sm_100a kernels of ``libmova_b200.so`` through :mod:`dualforce_b200.ops` -- there is no PyTorch compute path.
 
-Fusion plan per DiTBlock (13 launches instead of ~60 library kernels):
+Fusion plan per DiTBlock (17 launches instead of ~60 library kernels):
   add_to_f32(modulation + t_mod) -> LN+modulate -> QKV GEMM (one launch, packed weight) -> RMSNorm+RoPE (q, k in
   place) -> attention on strided q/k/v views -> o-proj GEMM with ``x + gate * (.)`` epilogue -> LN(affine) ->
   q GEMM -> RMSNorm -> [text k/v GEMM + RMSNorm] -> attention -> o-proj GEMM with residual epilogue ->

@@ -10,6 +10,7 @@ merge for the v2a bridge -- and returns the same full-length tensors as cp=1.
 """
 from __future__ import annotations
 
+import contextlib
 import types
 from typing import Optional, Sequence, Tuple
 
@@ -19,7 +20,7 @@ from . import cp as cpmod
 from . import ops, rope
 from .modules import ConditionalCrossAttentionBlock, DiTBlock, DualTowerConditionalBridge
 
-__all__ = ["forward_dual_tower_dit", "install", "CPRuntime", "GraphedForward"]
+__all__ = ["forward_dual_tower_dit", "install", "swap_modules", "CPRuntime", "GraphedForward"]
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -88,38 +89,47 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
     ops.rmsnorm_rope_(send[0][:, wd:2 * wd], nk, sa.norm_k.eps, head_dim=sa.head_dim, cos=cos, sin=sin,
                       rope_mode=ops.ROPE_INTERLEAVED, segments=plan.nseg, seg_stride=seg_stride)
     send = send.view(G, cp, Lc, 3 * wd)
-    main = torch.cuda.current_stream()
-    comm = rt.comm_stream
-    ready = torch.cuda.Event()
-    ready.record(main)
+    comm = rt.comm_stream  # None for CPU tensors (gloo host-logic tests): same exchanges, program order
+    main = torch.cuda.current_stream() if comm is not None else None
+
+    def on_comm():
+        return torch.cuda.stream(comm) if comm is not None else contextlib.nullcontext()
+
+    def record(stream):
+        if comm is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def wait(stream, ev):
+        if ev is not None:
+            stream.wait_event(ev)
+
+    ready = record(main)
     # every buffer is allocated on the compute stream; the side stream only fills it between two events
     L = sum(rows_per_rank)
     recv = [torch.empty(L, 3 * wd, dtype=torch.bfloat16, device=h.device) for _ in range(G)]
     back = torch.empty(G, cp, Lc, wd, dtype=torch.bfloat16, device=h.device)
     in_done = []
-    with torch.cuda.stream(comm):
-        comm.wait_event(ready)
+    with on_comm():
+        wait(comm, ready)
         for g in range(G):
             cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
-            ev = torch.cuda.Event()
-            ev.record(comm)
-            in_done.append(ev)
+            in_done.append(record(comm))
     outs, out_done = [], []
     for g in range(G):
-        main.wait_event(in_done[g])
+        wait(main, in_done[g])
         qkv = recv[g].unsqueeze(0)
         o = ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg)  # [1, L, wd]
         outs.append(o)
-        att = torch.cuda.Event()
-        att.record(main)
-        with torch.cuda.stream(comm):
-            comm.wait_event(att)
+        att = record(main)
+        with on_comm():
+            wait(comm, att)
             cpmod.gather_heads(o[0], rows_per_rank, rt.rank, rt.group, out=back[g])
-            ev = torch.cuda.Event()
-            ev.record(comm)
-            out_done.append(ev)
+            out_done.append(record(comm))
     for ev in out_done:
-        main.wait_event(ev)
+        wait(main, ev)
     return ops.linear(back.view(G * cp, Lc, wd), wo, sa.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x[0], gate=gate,
                       segments=plan.nseg).unsqueeze(0)
 
@@ -333,6 +343,16 @@ def install(pipe, cuda_graph: bool = False) -> int:
         _lib.require_device(torch.cuda.current_device())
     else:
         raise _lib.MovaB200Error("dualforce_b200.install: no CUDA device (the B200 path has no CPU fallback)")
+    count = swap_modules(pipe)
+    pipe.mova_b200_cuda_graph = bool(cuda_graph)
+    return count
+
+
+def swap_modules(pipe) -> int:
+    """The host-side half of :func:`install` (no device checks): replace DiTBlocks, bridge and heads by their B200
+    twins sharing the reference Parameters, bind ``forward_dual_tower_dit`` and ``inference_single_step``."""
+    from . import step
+
     count = 0
     for name in ("video_dit", "video_dit_2", "audio_dit"):
         model = getattr(pipe, name, None)
@@ -344,10 +364,9 @@ def install(pipe, cuda_graph: bool = False) -> int:
         count += len(pipe.dual_tower_bridge.audio_to_video_conditioners) + len(
             pipe.dual_tower_bridge.video_to_audio_conditioners)
     pipe.forward_dual_tower_dit = types.MethodType(forward_dual_tower_dit, pipe)
-    pipe.mova_b200_cuda_graph = bool(cuda_graph)
+    if not hasattr(pipe, "mova_b200_cuda_graph"):
+        pipe.mova_b200_cuda_graph = False
     # the step around the path (pipeline_mova.py:500-609): heads share the reference parameters
-    from . import step
-
     for name in ("video_dit", "video_dit_2", "audio_dit"):
         model = getattr(pipe, name, None)
         if model is not None and hasattr(model, "head") and not isinstance(model.head, step.Head):

@@ -1,0 +1,225 @@
+"""-m gpu: the denoising step around the dual-tower forward -- the four small kernels of csrc/step.cu
+and ``inference_single_step`` through the C ABI, against the CPU oracle, the reference's golden outputs
+(tests/golden/tiny_step.npz) and, at BASELINE.json sizes, exact index round trips.
+
+Written after this round's GPU budget was spent: the host logic is verified on CPU (tests/test_host_emulated.py,
+tests/test_cp_pipeline_gloo.py run the same Python with the kernels emulated), but the kernels of step.cu have not
+executed on hardware yet, hence the non-strict xfail mark -- XPASS on the B200 box is the expected outcome; drop the
+mark then."""
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mova_oracle as O
+from test_oracle_step_golden import load_step_case
+from util import assert_close, bf16_round, build_step_towers
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run pending (GPU budget of the round exhausted "
+                                                     "before csrc/step.cu existed); verified on CPU with emulated kernels")]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import dualforce_b200 as B
+
+    B._lib.require_device(0)
+    return B.ops
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("shape,patch", [((5, 6, 4, 9), (2, 2, 3)), ((36, 5, 44, 80), (1, 2, 2)), ((36, 49, 44, 80), (1, 2, 2)),
+                                         ((128, 403), (1,)), ((32, 21), (3,))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patchify_is_exact(ops, shape, patch, dtype):
+    """Pure index work + one bf16 rounding: bit-exact against the oracle's reshape/permute form, up to the full
+    360p latent [36, 49, 44, 80] (BASELINE.json configs[1])."""
+    x = rnd(*shape, seed=1, dtype=dtype)
+    got = ops.patchify(x.cuda(), patch).cpu()
+    p = tuple(patch) + (1, 1)
+    x5 = x.float().reshape(1, *shape) if len(shape) == 4 else x.float().reshape(1, *shape)
+    k = shape[0] * p[0] * p[1] * p[2]
+    eye = {"patch_embedding.weight": torch.eye(k).reshape(k, shape[0], *patch), "patch_embedding.bias": torch.zeros(k)}
+    ref, _ = O.patchify(eye, x5, patch)
+    assert torch.equal(got.float(), ref[0].to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("grid,patch,ch", [((3, 2, 3), (2, 2, 3), 7), ((49, 22, 40), (1, 2, 2), 16), ((403,), (1,), 128),
+                                           ((11,), (3,), 8)])
+def test_unpatchify_is_exact(ops, grid, patch, ch):
+    L, cols = math.prod(grid), math.prod(patch) * ch
+    y = rnd(L, cols, seed=2, dtype=torch.bfloat16)
+    got = ops.unpatchify(y.cuda(), grid, patch, ch).cpu()
+    assert torch.equal(got.float(), O.unpatchify(y.float()[None], grid, patch)[0])
+    # from a column slice of a wider buffer (row stride != row length)
+    buf = rnd(L, cols + 16, seed=3, dtype=torch.bfloat16).cuda()
+    got = ops.unpatchify(buf[:, 8:8 + cols], grid, patch, ch).cpu()
+    assert torch.equal(got.float(), O.unpatchify(buf[:, 8:8 + cols].float().cpu()[None], grid, patch)[0])
+
+
+def test_patchify_unpatchify_round_trip_at_360p(ops):
+    """Size-independent property at the full 360p geometry: cutting [16, 49, 88, 160] into (1,2,2) patches, moving the
+    channel to the innermost position and unpatchifying gives the input back bit for bit."""
+    x = rnd(16, 49, 88, 160, seed=4, dtype=torch.bfloat16).cuda()
+    cols = ops.patchify(x, (1, 2, 2))  # [L, 16*4] in (c, dt, dh, dw) order
+    L = cols.shape[0]
+    rows = cols.view(L, 16, 4).transpose(1, 2).contiguous().view(L, 64)  # -> (dt dh dw, c)
+    assert torch.equal(ops.unpatchify(rows, (49, 44, 80), (1, 2, 2), 16), x)
+
+
+@pytest.mark.parametrize("t", [0.0, 37.5, 900.0, 999.0])
+def test_sinusoidal_embedding(ops, t):
+    ts = torch.tensor([t], dtype=torch.float32)
+    got = ops.sinusoidal_embedding(256, ts.cuda()).cpu()
+    ref = O.sinusoidal_embedding_1d(256, ts)[0]
+    assert (got - ref).abs().max() <= 1e-6
+
+
+@pytest.mark.parametrize("N,K", [(8, 8), (5120, 256), (1536, 1536), (30720, 5120), (77, 136)])
+@pytest.mark.parametrize("pre,post", [(False, False), (True, False), (False, True)])
+def test_gemv_f32(ops, N, K, pre, post):
+    x = rnd(K, seed=5)
+    w = rnd(N, K, seed=6, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    b = rnd(N, seed=7, scale=0.1, dtype=torch.bfloat16)
+    xin = O.silu(x) if pre else x
+    ref = (w.double() @ xin.double() + b.double()).float()
+    if post:
+        ref = O.silu(ref)
+    got, got_bf = ops.gemv_f32(x.cuda(), w.cuda(), b.cuda(), pre_silu=pre, post_silu=post, want_bf16=True)
+    assert (got.cpu() - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(got_bf.cpu(), got.cpu().to(torch.bfloat16))
+    # strided weight (row slice of a wider matrix)
+    wide = rnd(N, K + 8, seed=8, scale=1 / math.sqrt(K), dtype=torch.bfloat16).cuda()
+    got2 = ops.gemv_f32(x.cuda(), wide[:, :K], None)
+    assert (got2.cpu() - (wide[:, :K].double().cpu() @ x.double()).float()).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ the step
+def _step_case():
+    cfg, Pv, Pa, Pb, inp, gold, meta = load_step_case()
+    Pv, Pa, Pb = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb)
+    inp = dict(inp, context=inp["context"].to(torch.bfloat16).float())
+    return cfg, Pv, Pa, Pb, inp, gold
+
+
+def test_step_pieces_vs_reference_golden():
+    from dualforce_b200 import step
+
+    cfg, Pv, Pa, Pb, inp, gold = _step_case()
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
+    ts = inp["timestep"].cuda()
+    t, t_mod = step.embed_time(vis, ts)
+    assert_close(t, gold["visual_t"], "t", ratio=8e-3, fro=6e-3)
+    assert_close(t_mod, gold["visual_t_mod"], "t_mod", ratio=8e-3, fro=6e-3)
+    ctx = step.embed_text(vis, inp["context"].to(torch.bfloat16).cuda())
+    assert_close(ctx, gold["visual_context"], "text embedding", ratio=1.5e-2, fro=8e-3)
+    tok, grid = step.patchify(vis, inp["visual_latents"].cuda())
+    assert_close(tok, gold["visual_tokens"], "video patchify", ratio=1.5e-2, fro=8e-3)
+    tok_a, (f,) = step.patchify(aud, inp["audio_latents"].cuda())
+    assert_close(tok_a, gold["audio_tokens"], "audio patchify", ratio=1.5e-2, fro=8e-3)
+    out = step.head_unpatchify(vis, gold["visual_tokens"].to(torch.bfloat16).cuda(),
+                               gold["visual_t"].to(torch.bfloat16).cuda(), grid)
+    assert_close(out, gold["visual_unpatchify"], "video head + unpatchify", ratio=1.5e-2, fro=8e-3)
+    out_a = step.head_unpatchify(aud, gold["audio_tokens"].to(torch.bfloat16).cuda(),
+                                 gold["audio_t"].to(torch.bfloat16).cuda(), (f,))
+    assert_close(out_a, gold["audio_unpatchify"], "audio head + unpatchify", ratio=1.5e-2, fro=8e-3)
+    assert_close(vis(inp["visual_latents"].cuda(), ts, inp["context"].to(torch.bfloat16).cuda()),
+                 gold["video_tower_forward"], "WanModel.forward", ratio=3e-2, fro=1.5e-2)
+
+
+def test_inference_single_step_vs_oracle_and_golden():
+    from dualforce_b200 import step
+
+    cfg, Pv, Pa, Pb, inp, gold = _step_case()
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
+    kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"].cuda(), audio_latents=inp["audio_latents"].cuda(),
+              context=inp["context"].to(torch.bfloat16).cuda(), timestep=inp["timestep"].cuda(), audio_timestep=None,
+              video_fps=cfg["video_fps"])
+    v, a = pipe.inference_single_step(**kw)
+    rv, ra = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], inp["context"],
+                                     inp["timestep"])
+    assert_close(v, rv, "step visual vs oracle", ratio=3e-2, fro=1.5e-2)
+    assert_close(a, ra, "step audio vs oracle", ratio=3e-2, fro=1.5e-2)
+    assert_close(v, gold["visual_output"], "step visual vs reference golden", ratio=4e-2, fro=2e-2)
+    assert_close(a, gold["audio_output"], "step audio vs reference golden", ratio=4e-2, fro=2e-2)
+    # memoised second call (text embeddings, per-layer text k/v, time embedding all served from the caches) is
+    # bit-identical to the first and to an uncached evaluation
+    v2, a2 = pipe.inference_single_step(**kw)
+    assert torch.equal(v, v2) and torch.equal(a, a2)
+    step.clear_step_caches(vis, aud)
+    v3, a3 = pipe.inference_single_step(**kw)
+    assert torch.equal(v, v3) and torch.equal(a, a3)
+
+
+def test_step_at_mova_widths_vs_oracle():
+    """MOVA widths (video 5120/40 heads, audio 1536/12, text 4096, freq 256, in 36 / out 16, audio 128 / 128) at one
+    layer per tower and a short clip the CPU oracle finishes in seconds."""
+    cfg = dict(O.REDUCED_360P_CFG, visual_layers=1, audio_layers=1, grid_size=(2, 22, 40), audio_len=17, text_len=512,
+               visual_in_dim=36, visual_out_dim=16, visual_patch=(1, 2, 2), audio_in_dim=128, audio_out_dim=128,
+               audio_patch=(1,), text_dim=4096, freq_dim=256, timestep=900.0)
+    Pv, Pa, Pb, inp = O.make_step_case(cfg, 21)
+    Pv, Pa, Pb = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb)
+    ctx = inp["context"].to(torch.bfloat16)
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
+    v, a = pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"].cuda(),
+                                      audio_latents=inp["audio_latents"].cuda(), context=ctx.cuda(),
+                                      timestep=inp["timestep"].cuda(), audio_timestep=None, video_fps=24.0)
+    rv, ra = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], ctx.float(),
+                                     inp["timestep"])
+    assert v.shape == (1, 16, 2, 44, 80) and a.shape == (1, 128, 17)
+    assert_close(v, rv, "360p-width step visual", ratio=3e-2, fro=1.5e-2)
+    assert_close(a, ra, "360p-width step audio", ratio=3e-2, fro=1.5e-2)
+
+
+# ------------------------------------------------------------------------------------------------ context parallel
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cp_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from cp_check import Mesh1D
+
+        cfg = dict(O.TINY_STEP_CFG, visual_dim=512, visual_heads=4, visual_ffn=768, grid_size=(3, 3, 5))
+        if cfg["visual_heads"] % world:
+            cfg = dict(cfg, visual_heads=world, visual_dim=128 * world, visual_ffn=256 * world)
+        Pv, Pa, Pb, inp = O.make_step_case(cfg, 77)
+        Pv, Pa, Pb = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb)
+        ctx = inp["context"].to(torch.bfloat16)
+        vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
+        kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"].cuda(), audio_latents=inp["audio_latents"].cuda(),
+                  context=ctx.cuda(), timestep=inp["timestep"].cuda(), audio_timestep=None, video_fps=cfg["video_fps"])
+        v, a = pipe.inference_single_step(**kw, cp_mesh=Mesh1D(dist.group.WORLD, rank, world))
+        torch.cuda.synchronize()
+        rv, ra = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], ctx.float(),
+                                         inp["timestep"])
+        assert_close(v, rv, f"cp{world} step visual (rank {rank})", ratio=3e-2, fro=1.5e-2)
+        assert_close(a, ra, f"cp{world} step audio (rank {rank})", ratio=3e-2, fro=1.5e-2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_step_context_parallel_world1():
+    """NCCL group of one: the sharded-head / narrow all-gather code path of the step on any single-GPU box."""
+    mp.spawn(_cp_worker, args=(1, _free_port()), nprocs=1, join=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_step_context_parallel_world2():
+    mp.spawn(_cp_worker, args=(2, _free_port()), nprocs=2, join=True)

@@ -1,0 +1,240 @@
+"""Host logic of the product (module twins, weight packing, stride plumbing, the dual-tower loop, the step wrapper and
+its memo caches) run on CPU through tests/emulated_ops.py -- a test-only stand-in for libmova_b200.so -- and checked
+against the oracle and the reference's golden outputs.  The CUDA kernels themselves are covered by the -m gpu tests."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import emulated_ops
+import mova_oracle as O
+import ref_loader
+from test_oracle_step_golden import load_step_case
+from util import assert_close, bf16_round, build_step_towers, build_towers, to_dev
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    import dualforce_b200 as B
+
+    B.rope.clear_cache()
+    return emulated_ops.install(monkeypatch)
+
+
+def test_dual_tower_forward_host_logic_vs_oracle_and_golden(emu):
+    with open(os.path.join(GOLDEN, "tiny_dual_tower.json")) as f:
+        meta = json.load(f)
+    cfg = meta["cfg"]
+    cfg["grid_size"] = tuple(cfg["grid_size"])
+    gold = np.load(os.path.join(GOLDEN, "tiny_dual_tower.npz"))
+    Pv, Pa, Pb, inp = O.make_case(cfg, meta["seed"])
+    Pv, Pa, Pb, inp = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb), bf16_round(inp)
+    vis, aud, bridge, pipe = build_towers(cfg, Pv, Pa, Pb, device="cpu")
+    d = to_dev(inp, device="cpu")
+    fv, fa = pipe.forward_dual_tower_dit(vis, d["visual_x"], d["audio_x"], d["visual_context"], d["audio_context"],
+                                         d["visual_t_mod"], d["audio_t_mod"], d["visual_freqs"], d["audio_freqs"],
+                                         cfg["grid_size"], cfg["video_fps"])
+    rv, ra = O.forward_dual_tower_dit(Pv, Pa, Pb, cfg, inp["visual_x"], inp["audio_x"], inp["visual_context"],
+                                      inp["audio_context"], inp["visual_t_mod"], inp["audio_t_mod"], inp["visual_freqs"],
+                                      inp["audio_freqs"], cfg["grid_size"], cfg["video_fps"])
+    assert_close(fv, rv, "visual vs oracle", ratio=3e-2, fro=1.2e-2)
+    assert_close(fa, ra, "audio vs oracle", ratio=3e-2, fro=1.2e-2)
+    assert_close(fv, torch.from_numpy(gold["final_visual"]), "visual vs reference golden", ratio=3e-2, fro=1.2e-2)
+    assert_close(fa, torch.from_numpy(gold["final_audio"]), "audio vs reference golden", ratio=3e-2, fro=1.2e-2)
+    # 17 launches per DiTBlock, 7 + 7 per bridge layer: nothing else may reach the device
+    n_blocks, n_bridge = cfg["visual_layers"] + cfg["audio_layers"], min(cfg["visual_layers"], cfg["audio_layers"])
+    assert sum(emu.values()) == 17 * n_blocks + 14 * n_bridge, emu
+    # inputs must not be mutated
+    assert torch.equal(d["visual_x"].float(), inp["visual_x"]) and torch.equal(d["audio_x"].float(), inp["audio_x"])
+
+
+@pytest.fixture()
+def step_case():
+    cfg, Pv, Pa, Pb, inp, gold, meta = load_step_case()
+    Pv, Pa, Pb = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb)
+    inp = dict(inp, context=inp["context"].to(torch.bfloat16).float())
+    return cfg, Pv, Pa, Pb, inp, gold, meta
+
+
+def test_patchify_index_math_is_exact(emu):
+    """The kernels' flat-index arithmetic (transcribed in emulated_ops) against the oracle's reshape/permute form."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 6, 4, 9, generator=g).to(torch.bfloat16)  # C, F, H, W with patch (2, 2, 3)
+    cols = emulated_ops.patchify(x, (2, 2, 3))
+    eye = {"patch_embedding.weight": torch.eye(60).reshape(60, 5, 2, 2, 3), "patch_embedding.bias": torch.zeros(60)}
+    ref, grid = O.patchify(eye, x.float()[None], (2, 2, 3))
+    assert grid == (3, 2, 3) and torch.equal(cols.float(), ref[0])
+    y = torch.randn(3 * 2 * 3, 2 * 2 * 3 * 7, generator=g).to(torch.bfloat16)
+    out = emulated_ops.unpatchify(y, grid, (2, 2, 3), 7)
+    assert torch.equal(out.float(), O.unpatchify(y.float()[None], grid, (2, 2, 3))[0])
+    # 1-D (audio) form, from a strided view
+    buf = torch.randn(11, 40, generator=g).to(torch.bfloat16)
+    out = emulated_ops.unpatchify(buf[:, 8:32], (11,), (3,), 8)
+    assert torch.equal(out.float(), O.unpatchify(buf[:, 8:32].float()[None], (11,), (3,))[0])
+
+
+def test_step_pieces_vs_reference_golden(emu, step_case):
+    import dualforce_b200 as B
+    from dualforce_b200 import step
+
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    t, t_mod = step.embed_time(vis, inp["timestep"])
+    assert t.dtype == torch.bfloat16 and t.shape == (1, cfg["visual_dim"]) and t_mod.shape == (1, 6, cfg["visual_dim"])
+    assert_close(t, gold["visual_t"], "t", ratio=8e-3, fro=6e-3)
+    assert_close(t_mod, gold["visual_t_mod"], "t_mod", ratio=8e-3, fro=6e-3)
+    ctx = step.embed_text(vis, inp["context"].to(torch.bfloat16))
+    assert_close(ctx, gold["visual_context"], "text embedding", ratio=1.5e-2, fro=8e-3)
+    tok, grid = step.patchify(vis, inp["visual_latents"])
+    assert tuple(grid) == cfg["grid_size"]
+    assert_close(tok, gold["visual_tokens"], "video patchify", ratio=1.5e-2, fro=8e-3)
+    tok_a, (f,) = step.patchify(aud, inp["audio_latents"])
+    assert f == cfg["audio_len"]
+    assert_close(tok_a, gold["audio_tokens"], "audio patchify", ratio=1.5e-2, fro=8e-3)
+    out = step.head_unpatchify(vis, gold["visual_tokens"].to(torch.bfloat16), gold["visual_t"].to(torch.bfloat16), grid)
+    assert_close(out, gold["visual_unpatchify"], "video head + unpatchify", ratio=1.5e-2, fro=8e-3)
+    out_a = step.head_unpatchify(aud, gold["audio_tokens"].to(torch.bfloat16), gold["audio_t"].to(torch.bfloat16), (f,))
+    assert_close(out_a, gold["audio_unpatchify"], "audio head + unpatchify", ratio=1.5e-2, fro=8e-3)
+    # RoPE tables as the reference pipeline assembles them
+    assert torch.equal(step.token_freqs(vis, grid, "cpu"), O.video_freqs(cfg["head_dim"], grid))
+    assert torch.equal(step.token_freqs(aud, (f,), "cpu"), O.audio_freqs(cfg["head_dim"], f))
+    # single-tower forwards (wan_video_dit.py:418-473)
+    assert_close(vis(inp["visual_latents"], inp["timestep"], inp["context"].to(torch.bfloat16)),
+                 gold["video_tower_forward"], "WanModel.forward", ratio=3e-2, fro=1.5e-2)
+    assert_close(aud(inp["audio_latents"], inp["timestep"], inp["context"].to(torch.bfloat16)),
+                 gold["audio_tower_forward"], "WanAudioModel.forward", ratio=3e-2, fro=1.5e-2)
+    assert B.WanModel is step.WanModel
+
+
+def test_inference_single_step_vs_oracle_and_golden(emu, step_case):
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    ctx = inp["context"].to(torch.bfloat16)
+    v, a = pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"],
+                                      audio_latents=inp["audio_latents"], context=ctx, timestep=inp["timestep"],
+                                      audio_timestep=None, video_fps=cfg["video_fps"])
+    assert v.dtype == torch.bfloat16 and v.shape == gold["visual_output"].shape and a.shape == gold["audio_output"].shape
+    rv, ra = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], inp["context"],
+                                     inp["timestep"])
+    assert_close(v, rv, "step visual vs oracle", ratio=3e-2, fro=1.5e-2)
+    assert_close(a, ra, "step audio vs oracle", ratio=3e-2, fro=1.5e-2)
+    assert_close(v, gold["visual_output"], "step visual vs reference golden", ratio=3e-2, fro=1.5e-2)
+    assert_close(a, gold["audio_output"], "step audio vs reference golden", ratio=3e-2, fro=1.5e-2)
+
+
+def test_step_memoises_prompt_and_timestep_work(emu, step_case):
+    """Second denoising step with the same two prompts: text embeddings and every layer's text k/v come from the
+    memo; within a step the negative call reuses the positive call's time embedding."""
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    pos = inp["context"].to(torch.bfloat16)
+    neg = torch.zeros_like(pos)
+
+    def one_step(ts):
+        outs = []
+        for ctx in (pos, neg):
+            before = dict(emu)
+            outs.append(pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"],
+                                                   audio_latents=inp["audio_latents"], context=ctx, timestep=ts,
+                                                   audio_timestep=None, video_fps=cfg["video_fps"]))
+            outs.append({k: emu.get(k, 0) - before.get(k, 0) for k in emu})
+        return outs
+
+    n_blocks = cfg["visual_layers"] + cfg["audio_layers"]
+    (v1, a1), c_pos1, (v1n, a1n), c_neg1 = one_step(torch.tensor([900.0]))
+    (v2, a2), c_pos2, (v2n, a2n), c_neg2 = one_step(torch.tensor([880.0]))
+    assert c_pos1["gemv_f32"] == 6 and c_pos1["sinusoidal_embedding"] == 2  # both towers
+    assert c_neg1.get("gemv_f32", 0) == 0 and c_neg1.get("sinusoidal_embedding", 0) == 0  # same timestep tensor
+    assert c_pos2["gemv_f32"] == 6  # new timestep
+    # text embedding: 2 GEMMs per tower; text k/v: one GEMM + one RMSNorm per block -- all skipped on step 2
+    assert c_pos1["linear"] - c_pos2["linear"] == 4 + n_blocks
+    assert c_neg1["linear"] - c_neg2["linear"] == 4 + n_blocks
+    assert c_pos1["rmsnorm_rope_"] - c_pos2["rmsnorm_rope_"] == n_blocks
+    # and the memo changes nothing: a fresh (uncached) evaluation of step 2 gives bit-identical outputs
+    from dualforce_b200 import step
+
+    step.clear_step_caches(vis, aud)
+    (v3, a3), _, (v3n, a3n), _ = one_step(torch.tensor([880.0]))
+    assert torch.equal(v2, v3) and torch.equal(a2, a3) and torch.equal(v2n, v3n) and torch.equal(a2n, a3n)
+    assert not torch.equal(v1, v2) and not torch.equal(v2, v2n)
+    # an in-place edit of the prompt bumps its version: no stale hit
+    pos.mul_(0.5)
+    (v4, _), c4, *_ = one_step(torch.tensor([880.0]))
+    assert c4["linear"] == c_pos1["linear"] and not torch.equal(v4, v2)
+
+
+def test_twin_state_dict_keys_equal_the_reference(step_case):
+    cfg, Pv, Pa, Pb, inp, gold, meta = step_case
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    assert sorted(vis.state_dict().keys()) == meta["reference_state_dict_keys"]["wan_model"]
+    assert sorted(aud.state_dict().keys()) == meta["reference_state_dict_keys"]["wan_audio_model"]
+
+
+def test_unsupported_step_options_fail_loudly(emu, step_case):
+    import dualforce_b200 as B
+
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    with pytest.raises(NotImplementedError):
+        B.WanModel(dim=256, in_dim=36, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6,
+                   patch_size=(1, 2, 2), num_heads=2, num_layers=1, has_image_input=True)
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    with pytest.raises(NotImplementedError):  # batch of 2 latents
+        pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"].repeat(2, 1, 1, 1, 1),
+                                   audio_latents=inp["audio_latents"], context=inp["context"].to(torch.bfloat16),
+                                   timestep=inp["timestep"], audio_timestep=None, video_fps=24.0)
+    with pytest.raises(NotImplementedError):  # per-token time embedding
+        vis.head(torch.zeros(1, 4, 256, dtype=torch.bfloat16), torch.zeros(1, 4, 256, dtype=torch.bfloat16))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_swap_modules_on_reference_pipeline_runs_the_reference_loop_shape(emu, step_case):
+    """dualforce_b200.install's host half on REAL reference towers: the swapped pipeline (reference WanModel
+    containers, B200 blocks / heads / bridge sharing their Parameters) reproduces the reference's own step."""
+    import make_golden
+    from dualforce_b200 import pipeline as pl
+    from dualforce_b200 import step
+
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    R, vis, aud, bridge, ref_pipe = make_golden.build_reference_step(cfg, Pv, Pa, Pb)
+    for m in (vis, aud, bridge):
+        m.to(torch.bfloat16)
+    pipe = types.SimpleNamespace(video_dit=vis, video_dit_2=None, audio_dit=aud, dual_tower_bridge=bridge,
+                                 _pre_forward=lambda m: None)
+    n = pl.swap_modules(pipe)
+    n_bridge = 2 * min(cfg["visual_layers"], cfg["audio_layers"])
+    assert n == cfg["visual_layers"] + cfg["audio_layers"] + n_bridge + 2
+    assert isinstance(vis.head, step.Head) and isinstance(pipe.dual_tower_bridge, pl.DualTowerConditionalBridge)
+    assert pl.swap_modules(pipe) == 0  # idempotent
+    v, a = pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"],
+                                      audio_latents=inp["audio_latents"], context=inp["context"].to(torch.bfloat16),
+                                      timestep=inp["timestep"], audio_timestep=None, video_fps=cfg["video_fps"])
+    assert_close(v, gold["visual_output"], "swapped reference pipeline, visual", ratio=3e-2, fro=1.5e-2)
+    assert_close(a, gold["audio_output"], "swapped reference pipeline, audio", ratio=3e-2, fro=1.5e-2)
+
+
+def test_bench_model_builder_composes_with_the_step(emu):
+    """bench.py builds the block lists exactly as the forward-level measurement always has and grafts them onto
+    zero-layer tower twins for the step-level e2e: the composition must run the step (host logic only here)."""
+    import bench
+
+    cfg = dict(O.TINY_CFG, grid_size=(2, 2, 3), audio_len=9)
+    pipe = bench.build_model(cfg, torch.device("cpu"), with_step=True)
+    assert len(pipe.video_dit.blocks) == cfg["visual_layers"] and len(pipe.audio_dit.blocks) == cfg["audio_layers"]
+    assert pipe.video_dit.patch_embedding.weight.dtype == torch.bfloat16
+    S = bench.STEP_360P
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, S["visual_in_dim"], 2, 4, 6, generator=g)
+    alat = torch.randn(1, S["audio_in_dim"], 9, generator=g)
+    ctx = torch.randn(1, cfg["text_len"], S["text_dim"], generator=g).to(torch.bfloat16)
+    v, a = pipe.inference_single_step(visual_dit=pipe.video_dit, visual_latents=lat, audio_latents=alat, context=ctx,
+                                      timestep=torch.tensor([900.0]), audio_timestep=None, video_fps=24.0)
+    assert v.shape == (1, S["visual_out_dim"], 2, 4, 6) and a.shape == (1, S["audio_out_dim"], 9)
+    assert torch.isfinite(v.float()).all() and torch.isfinite(a.float()).all()
+    # the forward-level builder is unchanged
+    bare = bench.build_model(cfg, torch.device("cpu"), with_step=False)
+    assert not hasattr(bare.video_dit, "patch_embedding") and not hasattr(bare, "inference_single_step")

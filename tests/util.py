@@ -38,6 +38,33 @@ def build_towers(cfg, Pv, Pa, Pb, device="cuda"):
     return vis, aud, bridge, pipe
 
 
+def build_step_towers(cfg, Pv, Pa, Pb, device="cuda"):
+    """dualforce_b200 WanModel / WanAudioModel / bridge twins holding step-level weights (oracle.make_step_case) in
+    bf16 on ``device`` + a pipeline-like namespace with both drop-in methods bound."""
+    import dualforce_b200 as B
+
+    common = dict(text_dim=cfg["text_dim"], freq_dim=cfg["freq_dim"], eps=cfg["eps"], has_image_input=False)
+    vis = B.WanModel(dim=cfg["visual_dim"], in_dim=cfg["visual_in_dim"], ffn_dim=cfg["visual_ffn"],
+                     out_dim=cfg["visual_out_dim"], patch_size=tuple(cfg["visual_patch"]), num_heads=cfg["visual_heads"],
+                     num_layers=cfg["visual_layers"], **common)
+    aud = B.WanAudioModel(dim=cfg["audio_dim"], in_dim=cfg["audio_in_dim"], ffn_dim=cfg["audio_ffn"],
+                          out_dim=cfg["audio_out_dim"], patch_size=list(cfg["audio_patch"]), num_heads=cfg["audio_heads"],
+                          num_layers=cfg["audio_layers"], vae_type="dac", **common)
+    bridge = B.DualTowerConditionalBridge(
+        visual_layers=cfg["visual_layers"], audio_layers=cfg["audio_layers"], visual_hidden_dim=cfg["visual_dim"],
+        audio_hidden_dim=cfg["audio_dim"], audio_fps=cfg["audio_fps"], head_dim=cfg["head_dim"],
+        interaction_strategy=cfg["interaction_strategy"], apply_cross_rope=cfg["apply_cross_rope"])
+    vis.load_state_dict(Pv, strict=True)
+    aud.load_state_dict(Pa, strict=True)
+    bridge.load_state_dict(Pb, strict=True)
+    for m in (vis, aud, bridge):
+        m.to(device=device, dtype=torch.bfloat16)
+    pipe = types.SimpleNamespace(audio_dit=aud, dual_tower_bridge=bridge, video_dit=vis, video_dit_2=None)
+    pipe.forward_dual_tower_dit = types.MethodType(B.forward_dual_tower_dit, pipe)
+    pipe.inference_single_step = types.MethodType(B.inference_single_step, pipe)
+    return vis, aud, bridge, pipe
+
+
 def to_dev(inp, device="cuda"):
     out = {}
     for k, v in inp.items():
