@@ -55,6 +55,7 @@ SIGNATURES = {
     "mova_b200_unpatchify": (
         c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mova_b200_sinusoidal": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "mova_b200_cfg_euler": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
     "mova_b200_gemv_f32": (
         c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }

@@ -12,6 +12,9 @@
 //                  reference runs under autocast(float32) (pipeline_mova.py:544-549): fp32 activations,
 //                  bf16-valued weights, fp32 accumulation, SiLU fused on either side.
 //
+//   * cfg_euler:   classifier-free-guidance combine + flow-match Euler update of the latents in one pass
+//                  (pipeline_mova.py:456-460; schedulers/flow_match_pair.py:213-227).
+//
 // All of them are HBM-bound byte movers: coalesced 16-byte accesses on the large side, one pass.
 #include "common.cuh"
 #include "host_utils.h"
@@ -128,9 +131,77 @@ gemv_f32_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ W
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// classifier-free guidance + flow-match Euler update, one pass (pipeline_mova.py:456-460 + flow_match_pair.py:213-227):
+//   out = sample + (nega + s * (posi - nega)) * dsigma          (nega == nullptr: out = sample + posi * dsigma)
+// predictions bf16 (converted with .float() by the reference), latents fp32; 8 elements per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cfg_euler_kernel(const __nv_bfloat16* __restrict__ posi, const __nv_bfloat16* __restrict__ nega,
+                 const float* __restrict__ sample, float* __restrict__ out, long long n, float cfg_scale,
+                 float dsigma) {
+  const long long i0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  if (i0 + 8 <= n) {
+    const uint4 up = *reinterpret_cast<const uint4*>(posi + i0);
+    const uint32_t pw[4] = {up.x, up.y, up.z, up.w};
+    uint32_t nw[4] = {0, 0, 0, 0};
+    if (nega != nullptr) {
+      const uint4 un = *reinterpret_cast<const uint4*>(nega + i0);
+      nw[0] = un.x; nw[1] = un.y; nw[2] = un.z; nw[3] = un.w;
+    }
+    const float4 s0 = *reinterpret_cast<const float4*>(sample + i0);
+    const float4 s1 = *reinterpret_cast<const float4*>(sample + i0 + 4);
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float p0 = bf16lo(pw[e]), p1 = bf16hi(pw[e]);
+      float g0 = p0, g1 = p1;
+      if (nega != nullptr) {
+        const float n0 = bf16lo(nw[e]), n1 = bf16hi(nw[e]);
+        g0 = n0 + cfg_scale * (p0 - n0);
+        g1 = n1 + cfg_scale * (p1 - n1);
+      }
+      r[2 * e] = sv[2 * e] + g0 * dsigma;
+      r[2 * e + 1] = sv[2 * e + 1] + g1 * dsigma;
+    }
+    *reinterpret_cast<float4*>(out + i0) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(out + i0 + 4) = make_float4(r[4], r[5], r[6], r[7]);
+  } else {
+    for (long long i = i0; i < n; ++i) {
+      const float pv = __bfloat162float(posi[i]);
+      float g = pv;
+      if (nega != nullptr) {
+        const float nv = __bfloat162float(nega[i]);
+        g = nv + cfg_scale * (pv - nv);
+      }
+      out[i] = sample[i] + g * dsigma;
+    }
+  }
+}
+
 }  // namespace mv
 
 extern "C" {
+
+int mova_b200_cfg_euler(const void* posi, const void* nega, const float* sample, float* out, int64_t n,
+                        float cfg_scale, float dsigma, void* stream) {
+  using namespace mv;
+  MV_REQUIRE(posi && sample && out, "mova_b200_cfg_euler: null pointer");
+  MV_REQUIRE(((reinterpret_cast<uintptr_t>(posi) | reinterpret_cast<uintptr_t>(nega) |
+               reinterpret_cast<uintptr_t>(sample) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "mova_b200_cfg_euler: operands must be 16-byte aligned");
+  if (n <= 0) return 0;
+  const int threads = 256;
+  const long long groups = (n + 7) / 8;
+  const unsigned blocks = static_cast<unsigned>((groups + threads - 1) / threads);
+  cfg_euler_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(posi), static_cast<const __nv_bfloat16*>(nega), sample, out, n, cfg_scale,
+      dsigma);
+  MV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int mova_b200_patchify(const void* x, int x_is_f32, int C, int F, int H, int W, int pt, int ph, int pw, void* out,
                        int64_t ldo, void* stream) {

@@ -29,7 +29,7 @@ from . import ops, rope
 __all__ = [
     "AttentionModule", "USPAttention", "SelfAttention", "CrossAttention", "GateModule", "DiTBlock", "ConditionalCrossAttention",
     "ConditionalCrossAttentionBlock", "CrossModalInteractionController", "RotaryEmbedding",
-    "DualTowerConditionalBridge",
+    "DualTowerConditionalBridge", "merged_linear",
 ]
 
 
@@ -48,6 +48,27 @@ def _pack_linears(linears: List[nn.Linear]) -> Tuple[torch.Tensor, Optional[torc
             l.bias.data = b[row:row + n]
         row += n
     return w, b
+
+
+def merged_linear(layer: nn.Module) -> nn.Linear:
+    """A plain ``nn.Linear`` for ``layer``.  The reference's LoRA wrapper (``LoRALinear``: ``original_layer``,
+    ``lora_A``, ``lora_B``, ``scaling``; engine/trainer/accelerate/lora_utils.py:19-109) computes
+    ``W x + scaling * B (A x)``; the kernels take one weight, so the adapter is folded in exactly as the reference's own
+    ``merge_weights`` / ``MOVALoRA.merge_lora_weights`` does (lora_utils.py:95-109, pipelines/mova_lora.py:190-220):
+    ``W' = W + scaling * B A`` -- evaluated in fp32 and rounded once to the weight dtype.  A plain ``nn.Linear`` is
+    returned unchanged (same object, so its Parameters stay shared with the reference module)."""
+    if isinstance(layer, nn.Linear):
+        return layer
+    if all(hasattr(layer, a) for a in ("original_layer", "lora_A", "lora_B", "scaling")):
+        base = merged_linear(layer.original_layer)
+        w = base.weight.data
+        delta = (layer.lora_B.weight.data.float() @ layer.lora_A.weight.data.float()) * float(layer.scaling)
+        out = nn.Linear(base.in_features, base.out_features, bias=base.bias is not None, device="meta")
+        out.weight = nn.Parameter((w.float() + delta.to(w.device)).to(w.dtype), requires_grad=False)
+        if base.bias is not None:
+            out.bias = nn.Parameter(base.bias.data.clone(), requires_grad=False)
+        return out
+    raise TypeError(f"expected nn.Linear or a LoRA-wrapped linear, got {type(layer).__module__}.{type(layer).__name__}")
 
 
 class _Packed:
@@ -224,14 +245,16 @@ class DiTBlock(nn.Module):
         nn.Module.__init__(blk.self_attn)
         sa, rsa = blk.self_attn, ref.self_attn
         sa.dim, sa.num_heads, sa.head_dim = rsa.dim, rsa.num_heads, rsa.head_dim
-        sa.q, sa.k, sa.v, sa.o, sa.norm_q, sa.norm_k = rsa.q, rsa.k, rsa.v, rsa.o, rsa.norm_q, rsa.norm_k
+        sa.q, sa.k, sa.v, sa.o = (merged_linear(m) for m in (rsa.q, rsa.k, rsa.v, rsa.o))
+        sa.norm_q, sa.norm_k = rsa.norm_q, rsa.norm_k
         sa.attn = AttentionModule(rsa.num_heads)
         sa._qkv = _Packed()
         blk.cross_attn = CrossAttention.__new__(CrossAttention)
         nn.Module.__init__(blk.cross_attn)
         ca, rca = blk.cross_attn, ref.cross_attn
         ca.dim, ca.num_heads, ca.head_dim = rca.dim, rca.num_heads, rca.head_dim
-        ca.q, ca.k, ca.v, ca.o, ca.norm_q, ca.norm_k = rca.q, rca.k, rca.v, rca.o, rca.norm_q, rca.norm_k
+        ca.q, ca.k, ca.v, ca.o = (merged_linear(m) for m in (rca.q, rca.k, rca.v, rca.o))
+        ca.norm_q, ca.norm_k = rca.norm_q, rca.norm_k
         ca.has_image_input = False
         ca.attn = AttentionModule(rca.num_heads)
         ca._kv = _Packed()
@@ -407,7 +430,8 @@ class ConditionalCrossAttentionBlock(nn.Module):
         nn.Module.__init__(inner)
         r = ref.inner
         inner.q_dim, inner.kv_dim, inner.num_heads, inner.head_dim = r.q_dim, r.kv_dim, r.num_heads, r.head_dim
-        inner.q, inner.k, inner.v, inner.o, inner.norm_q, inner.norm_k = r.q, r.k, r.v, r.o, r.norm_q, r.norm_k
+        inner.q, inner.k, inner.v, inner.o = (merged_linear(m) for m in (r.q, r.k, r.v, r.o))
+        inner.norm_q, inner.norm_k = r.norm_q, r.norm_k
         inner.attn = AttentionModule(r.num_heads)
         inner._kv = _Packed()
         blk.inner = inner

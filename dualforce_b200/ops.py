@@ -14,7 +14,7 @@ from ._lib import EPI_BIAS, EPI_GELU_TANH, EPI_RESIDUAL, ROPE_HALF, ROPE_INTERLE
 
 __all__ = [
     "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32", "patchify", "unpatchify",
-    "sinusoidal_embedding", "gemv_f32",
+    "sinusoidal_embedding", "gemv_f32", "cfg_euler_step",
     "EPI_BIAS", "EPI_GELU_TANH", "EPI_RESIDUAL", "ROPE_NONE", "ROPE_INTERLEAVED", "ROPE_HALF",
 ]
 
@@ -351,3 +351,31 @@ def gemv_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
                                         _stream())
     _lib.check(rc, "mova_b200_gemv_f32")
     return (y, yb) if want_bf16 else y
+
+
+def cfg_euler_step(posi: torch.Tensor, nega: Optional[torch.Tensor], sample: torch.Tensor, cfg_scale: float,
+                   dsigma: float, *, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``sample + (nega + cfg_scale * (posi - nega)) * dsigma`` in one pass: the classifier-free-guidance combine of
+    pipeline_mova.py:456-460 fused with ``FlowMatchPairScheduler.step_from_to`` (schedulers/flow_match_pair.py:213-227;
+    ``dsigma = sigma_to - sigma_from`` from the reference's scheduler).  ``posi`` / ``nega``: bf16 model outputs
+    (``nega=None``: ``cfg_scale == 1`` path, :439-441), ``sample``: fp32 latents; returns fp32 (``out`` may be ``sample``)."""
+    _need(posi, torch.bfloat16, "posi")
+    _need(sample, torch.float32, "sample")
+    if posi.shape != sample.shape or not posi.is_contiguous() or not sample.is_contiguous():
+        raise _lib.MovaB200Error(f"cfg_euler_step: posi {tuple(posi.shape)} and sample {tuple(sample.shape)} must be "
+                                 "contiguous and of one shape")
+    nptr = None
+    if nega is not None:
+        _need(nega, torch.bfloat16, "nega")
+        if nega.shape != posi.shape or not nega.is_contiguous():
+            raise _lib.MovaB200Error("cfg_euler_step: nega must match posi")
+        nptr = nega.data_ptr()
+    if out is None:
+        out = torch.empty_like(sample)
+    _need(out, torch.float32, "out")
+    if out.shape != sample.shape or not out.is_contiguous():
+        raise _lib.MovaB200Error("cfg_euler_step: bad `out`")
+    rc = _lib.load().mova_b200_cfg_euler(posi.data_ptr(), nptr, sample.data_ptr(), out.data_ptr(), sample.numel(),
+                                         float(cfg_scale), float(dsigma), _stream())
+    _lib.check(rc, "mova_b200_cfg_euler")
+    return out

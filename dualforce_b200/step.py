@@ -39,7 +39,7 @@ from . import ops, rope
 from .modules import DiTBlock
 
 __all__ = ["Head", "WanModel", "WanAudioModel", "inference_single_step", "embed_time", "embed_text", "patchify",
-           "head_unpatchify", "clear_step_caches"]
+           "head_unpatchify", "guided_update", "clear_step_caches"]
 
 _STATIC_FLAG = "_mova_b200_static"  # set on context embeddings whose per-layer k / v may be memoised
 
@@ -382,6 +382,22 @@ def inference_single_step(self, visual_dit, visual_latents: torch.Tensor, audio_
     visual_output = head_unpatchify(visual_dit, visual_x, visual_t, grid_size, rows, group)
     audio_output = head_unpatchify(audio_dit, audio_x, audio_t, (f,))
     return visual_output, audio_output
+
+
+def guided_update(noise_pred_posi: torch.Tensor, noise_pred_nega: Optional[torch.Tensor], sample: torch.Tensor,
+                  cfg_scale: float, sigma_from, sigma_to, *, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """What ``MOVA.__call__`` does with the two predictions of one scheduler iteration, in one kernel:
+    ``noise = nega + cfg_scale * (posi - nega)`` (pipeline_mova.py:456-460; ``noise_pred_nega=None`` is the
+    ``cfg_scale == 1`` branch, :439-441) followed by ``FlowMatchPairScheduler.step_from_to``
+    (schedulers/flow_match_pair.py:213-227): ``sample + noise * (sigma_to - sigma_from)``.  The sigmas come from the
+    reference's scheduler (``scheduler.timestep_to_sigma``; ``sigma_to = 0`` after the last step).  ``sample`` is the
+    fp32 latent tensor; the result is fp32 and may be written in place (``out=sample``)."""
+    dsigma = float(sigma_to) - float(sigma_from)
+    posi = noise_pred_posi.contiguous()
+    nega = noise_pred_nega.contiguous() if noise_pred_nega is not None else None
+    if sample.dtype != torch.float32:
+        raise TypeError(f"guided_update: latents are kept in fp32 by the pipeline (pipeline_mova.py:378-399), got {sample.dtype}")
+    return ops.cfg_euler_step(posi, nega, sample, float(cfg_scale), dsigma, out=out)
 
 
 def bind(pipe) -> None:

@@ -161,6 +161,17 @@ int mova_b200_sinusoidal(const float* t, float* out, int dim, void* stream);
 int mova_b200_gemv_f32(const float* x, const void* W, int64_t ldw, const void* bias, float* y, void* y_bf16, int N,
                        int K, int pre_act, int post_act, void* stream);
 
+/*
+ * Classifier-free guidance + flow-match Euler update in one pass:
+ *   out = sample + (nega + cfg_scale * (posi - nega)) * dsigma        (nega == NULL: out = sample + posi * dsigma)
+ * Replaces `nega.float() + cfg_scale * (posi.float() - nega.float())` (pipeline_mova.py:456-460) and
+ * FlowMatchPairScheduler.step_from_to's `sample + model_output * (sigma_to - sigma_from)`
+ * (schedulers/flow_match_pair.py:213-227); dsigma = sigma_to - sigma_from comes from the reference's scheduler.
+ *   posi/nega bf16 [n], sample/out fp32 [n] (out may alias sample); all 16-byte aligned
+ */
+int mova_b200_cfg_euler(const void* posi, const void* nega, const float* sample, float* out, int64_t n,
+                        float cfg_scale, float dsigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

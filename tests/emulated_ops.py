@@ -274,9 +274,24 @@ def gemv_f32(x, weight, bias=None, *, pre_silu=False, post_silu=False, want_bf16
     return (y, y.to(BF16)) if want_bf16 else y
 
 
+def cfg_euler_step(posi, nega, sample, cfg_scale, dsigma, *, out=None):
+    _count("cfg_euler_step")
+    _need(posi, BF16, "posi"); _need(sample, F32, "sample")
+    g = posi.float()
+    if nega is not None:
+        _need(nega, BF16, "nega")
+        g = nega.float() + float(cfg_scale) * (posi.float() - nega.float())
+    res = sample + g * float(dsigma)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
 ENTRY_POINTS = dict(linear=linear, attention=attention, layernorm=layernorm, rmsnorm_rope_=rmsnorm_rope_,
                     lse_merge=lse_merge, add_to_f32=add_to_f32, patchify=patchify, unpatchify=unpatchify,
-                    sinusoidal_embedding=sinusoidal_embedding, gemv_f32=gemv_f32)
+                    sinusoidal_embedding=sinusoidal_embedding, gemv_f32=gemv_f32,
+                    cfg_euler_step=cfg_euler_step)
 
 
 def install(monkeypatch):

@@ -104,6 +104,21 @@ def test_gemv_f32(ops, N, K, pre, post):
     assert (got2.cpu() - (wide[:, :K].double().cpu() @ x.double()).float()).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("n", [(1, 16, 49, 44, 80), (1, 128, 403), (3, 5, 7)])
+@pytest.mark.parametrize("with_nega", [True, False])
+def test_cfg_euler_step(ops, n, with_nega):
+    """CFG combine + Euler update at the real latent sizes (video [1,16,49,44,80], audio [1,128,403]) and a ragged
+    tail; fp32 arithmetic, fused multiply-adds may differ from torch's sequence by an ulp."""
+    posi, nega = rnd(*n, seed=1, dtype=torch.bfloat16), rnd(*n, seed=2, dtype=torch.bfloat16)
+    lat = rnd(*n, seed=3)
+    ref = O.guided_update(posi, nega if with_nega else None, lat, 5.0, 0.91, 0.87)
+    lat_dev = lat.cuda()
+    got = ops.cfg_euler_step(posi.cuda(), nega.cuda() if with_nega else None, lat_dev, 5.0, 0.87 - 0.91)
+    assert (got.cpu() - ref).abs().max() <= 2e-6 * max(1.0, ref.abs().max().item())
+    ops.cfg_euler_step(posi.cuda(), nega.cuda() if with_nega else None, lat_dev, 5.0, 0.87 - 0.91, out=lat_dev)
+    assert torch.equal(lat_dev, got)  # in place gives the same bits
+
+
 # ------------------------------------------------------------------------------------------------ the step
 def _step_case():
     cfg, Pv, Pa, Pb, inp, gold, meta = load_step_case()

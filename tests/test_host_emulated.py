@@ -238,3 +238,64 @@ def test_bench_model_builder_composes_with_the_step(emu):
     # the forward-level builder is unchanged
     bare = bench.build_model(cfg, torch.device("cpu"), with_step=False)
     assert not hasattr(bare.video_dit, "patch_embedding") and not hasattr(bare, "inference_single_step")
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_lora_wrapped_reference_block_is_merged_at_install(emu):
+    """a reference block whose q/k/v/o were wrapped by the reference's own inject_lora_to_model
+    (engine/trainer/accelerate/lora_utils.py) is swapped with the adapters folded into the weights; the result
+    matches the reference's un-merged LoRA forward."""
+    import importlib.util
+    import sys
+
+    import dualforce_b200 as B
+
+    R = ref_loader.load()
+    sys.modules["diffusers"].DiffusionPipeline = object  # lora_utils.py imports the name only
+    spec = importlib.util.spec_from_file_location(
+        "ref_lora_utils", os.path.join(ref_loader.REFERENCE_ROOT, "mova/engine/trainer/accelerate/lora_utils.py"))
+    lora_utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lora_utils)
+
+    cfg = O.TINY_CFG
+    Pv, Pa, Pb, inp = O.make_case(cfg, 5)
+    Pv, inp = bf16_round(Pv), bf16_round(inp)
+    blk = R.wan_video_dit.DiTBlock(False, cfg["visual_dim"], cfg["visual_heads"], cfg["visual_ffn"], cfg["eps"])
+    blk.load_state_dict({k[len("blocks.0."):]: v for k, v in Pv.items() if k.startswith("blocks.0.")})
+    layers = lora_utils.inject_lora_to_model(blk, rank=4, alpha=8.0, target_modules=["q", "k", "v", "o"])
+    assert len(layers) == 8  # q, k, v, o of self_attn and cross_attn
+    g = torch.Generator().manual_seed(9)
+    for l in layers.values():
+        l.lora_B.weight.data = (torch.randn(l.lora_B.weight.shape, generator=g) * 0.2).to(torch.bfloat16).float()
+        l.lora_A.weight.data = l.lora_A.weight.data.to(torch.bfloat16).float()
+    with torch.no_grad():
+        ref = blk(inp["visual_x"], inp["visual_context"], inp["visual_t_mod"], inp["visual_freqs"])
+        plain = O.dit_block(Pv, "blocks.0", inp["visual_x"], inp["visual_context"], inp["visual_t_mod"],
+                            inp["visual_freqs"], cfg["visual_heads"], cfg["eps"])
+    assert (ref - plain).abs().max() > 0.05  # the adapters do change the output
+    blk.to(torch.bfloat16)
+    mine = B.DiTBlock.from_reference(blk)
+    assert isinstance(mine.self_attn.q, torch.nn.Linear) and isinstance(mine.cross_attn.o, torch.nn.Linear)
+    d = to_dev(inp, device="cpu")
+    got = mine(d["visual_x"], d["visual_context"], d["visual_t_mod"], d["visual_freqs"])
+    assert_close(got, ref, "LoRA-merged block vs reference LoRA forward", ratio=2e-2, fro=8e-3)
+    with pytest.raises(TypeError):
+        B.modules.merged_linear(torch.nn.Identity())
+
+
+def test_guided_update_host_logic(emu):
+    from dualforce_b200 import step
+
+    g = torch.Generator().manual_seed(4)
+    posi = torch.randn(1, 16, 3, 8, 10, generator=g).to(torch.bfloat16)
+    nega = torch.randn(1, 16, 3, 8, 10, generator=g).to(torch.bfloat16)
+    lat = torch.randn(1, 16, 3, 8, 10, generator=g)
+    ref = O.guided_update(posi, nega, lat, 5.0, 0.9, 0.85)
+    got = step.guided_update(posi, nega, lat, 5.0, 0.9, 0.85)
+    assert got.dtype == torch.float32 and (got - ref).abs().max() <= 1e-6
+    # cfg_scale == 1 branch and the in-place form the denoising loop uses (a persistent [latents | condition] buffer)
+    buf = torch.cat([lat, torch.zeros(1, 20, 3, 8, 10)], dim=1)
+    out = step.guided_update(posi, None, buf[:, :16], 1.0, 0.9, 0.0, out=buf[:, :16])
+    assert out.data_ptr() == buf.data_ptr() and (buf[:, :16] - O.guided_update(posi, None, lat, 1.0, 0.9, 0.0)).abs().max() <= 1e-6
+    with pytest.raises(TypeError):
+        step.guided_update(posi, nega, lat.to(torch.bfloat16), 5.0, 0.9, 0.85)
