@@ -47,7 +47,8 @@ constexpr int AT_BAR_KVEMPTY = AT_BAR_KVFULL + AT_NS;  // [NS]
 constexpr int AT_BAR_SFULL = AT_BAR_KVEMPTY + AT_NS;   // [2]
 constexpr int AT_BAR_PREADY = AT_BAR_SFULL + 2;        // [tile][half of the key block] = [4]
 constexpr int AT_BAR_ODONE = AT_BAR_PREADY + 4;        // [2]
-constexpr int AT_NUM_BARS = AT_BAR_ODONE + 2;
+constexpr int AT_BAR_SLOADED = AT_BAR_ODONE + 2;       // [2] (QSPLIT > 0: softmax has the score tile in registers)
+constexpr int AT_NUM_BARS = AT_BAR_SLOADED + 2;
 constexpr int AT_OFF_TMEM_PTR = AT_OFF_BARS + AT_NUM_BARS * 8;
 constexpr int AT_SMEM_BYTES = AT_OFF_TMEM_PTR + 16;
 static_assert(AT_SMEM_BYTES <= 232448, "attention shared memory budget exceeded");
@@ -58,7 +59,15 @@ constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 constexpr int AT_DEFAULT_EMU = 4;
 
 // EMU: how many of every 16 score pairs take the polynomial path (0 = all MUFU, 8 = half and half)
-template <int EMU, bool TRACE>
+// QSPLIT (experimental, MOVA_ATTN_VARIANT=v7 / v8; 0 = the shipped v3 schedule): Q.K^T of block j+1 is issued in
+// N-slices so that only the slice that overwrites the last-consumed part of P(j) stays on the critical path:
+//   keys 64..127 -> columns 64..127, which hold no P: issued as soon as the softmax warps have S(j) in registers
+//                   (new barrier SLOADED), i.e. it runs in what used to be tensor-pipe idle time;
+//   keys 0..63   -> columns 0..63 (= P): QSPLIT 1: one N=64 slice after P.V(j);
+//                   QSPLIT 2: keys 0..31 after the first half of P.V(j), keys 32..63 after the second.
+// tcgen05.mma cost is linear in N (floor 128*N/256 cycles per K=16 step), so the tensor work is unchanged while the
+// dependent chain  P(j) ready -> S(j+1) ready  shrinks from P.V half + 512 cycles to P.V half + 256 (128) cycles.
+template <int EMU, bool TRACE, int QSPLIT>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -100,6 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(bar(AT_BAR_PREADY + 2 * i), 4);  // one arrive per softmax warp
       mbar_init(bar(AT_BAR_PREADY + 2 * i + 1), 4);
       mbar_init(bar(AT_BAR_ODONE + i), 1);
+      mbar_init(bar(AT_BAR_SLOADED + i), 4);
     }
     fence_barrier_init();
   }
@@ -132,6 +142,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld_x32(t_s + q * 32, reinterpret_cast<uint32_t(&)[32]>(s[q * 32]));
         tmem_wait_ld();
+        if constexpr (QSPLIT > 0) {
+          // the score tile is in registers: columns 64..127 may take the upper half of S(j+1)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(AT_BAR_SLOADED + tile));
+        }
         if ((threadIdx.x & 127) == 0) ev(tile, 2);
         if (j == n_kv - 1 && tail < 128) {
 #pragma unroll
@@ -299,6 +315,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         __syncwarp();
       };
+      // S[:, n0 : n0 + N] = Q . K[n0 : n0 + N]^T  (N = 64 or 32): rows n0.. of the K tile start n0 * 128 bytes into
+      // each 64-column swizzle panel (a multiple of the 1024-byte swizzle atom), accumulator columns n0..n0+N-1
+      auto issue_qk_slice = [&](int tile, uint32_t kbase, int n0, uint32_t idesc, bool commit_sfull) {
+        const uint64_t qd = umma_desc_k_sw128(smem_base + AT_OFF_Q + tile * AT_TILE_BYTES);
+        const uint64_t kd = umma_desc_k_sw128(kbase + n0 * 128);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t off16 = ((ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32) >> 4;
+            umma_ss<1>(tmem_u + AT_TMEM_S + tile * 128 + n0, qd + off16, kd + off16, idesc, ks > 0 ? 1u : 0u);
+          }
+          if (commit_sfull) umma_commit(bar(AT_BAR_SFULL + tile));
+        }
+        __syncwarp();
+      };
       // P.V over keys [64*half, 64*half + 64) of the block
       auto issue_pv_half = [&](int tile, uint32_t vbase, int half, bool acc) {
         const uint64_t vd = umma_desc_mn_sw128(vbase + half * 8192, AT_HALF_BYTES, 1024);
@@ -340,23 +371,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t kslot = slot;
         const uint32_t kphase = phase;
         for (int tile = 0; tile < nt; ++tile) {
+          if constexpr (QSPLIT > 0) {
+            if (!last) {
+              constexpr uint32_t IDESC_QK64 = umma_idesc_bf16(128, 64, 0, 0);
+              if (tile == 0) {
+                mbar_wait(bar(AT_BAR_KVFULL + kslot), kphase);
+                tc_fence_after();
+              }
+              // upper half of S(j+1) into the columns P(j) does not use, as soon as S(j) has been read
+              mbar_wait(bar(AT_BAR_SLOADED + tile), j & 1);
+              tc_fence_after();
+              issue_qk_slice(tile, slot_addr(kslot), 64, IDESC_QK64, false);
+            }
+          }
           // one barrier per half of P: a single two-phase barrier would let the softmax run two phases ahead of
           // this warp, which a parity wait cannot tell apart from "not there yet"
           mbar_wait(bar(AT_BAR_PREADY + 2 * tile), j & 1);
           tc_fence_after();
           if (tile == 0) ev(2, 10); else ev(2, 11);
           issue_pv_half(tile, slot_addr(vslot), 0, j > 0);
+          if constexpr (QSPLIT == 2) {
+            // keys 0..31 overwrite the half of P the MMAs just issued consume (the tensor pipe runs in issue order)
+            if (!last) issue_qk_slice(tile, slot_addr(kslot), 0, umma_idesc_bf16(128, 32, 0, 0), false);
+          }
           mbar_wait(bar(AT_BAR_PREADY + 2 * tile + 1), j & 1);
           tc_fence_after();
           issue_pv_half(tile, slot_addr(vslot), 1, true);
           if (tile == 0) ev(2, 12); else ev(2, 13);
           if (last) commit(bar(AT_BAR_ODONE + tile));
           if (!last) {
-            if (tile == 0) {
-              mbar_wait(bar(AT_BAR_KVFULL + kslot), kphase);
-              tc_fence_after();
+            if constexpr (QSPLIT == 0) {
+              if (tile == 0) {
+                mbar_wait(bar(AT_BAR_KVFULL + kslot), kphase);
+                tc_fence_after();
+              }
+              issue_qk(tile, slot_addr(kslot));
+            } else if constexpr (QSPLIT == 1) {
+              issue_qk_slice(tile, slot_addr(kslot), 0, umma_idesc_bf16(128, 64, 0, 0), true);
+            } else {
+              issue_qk_slice(tile, slot_addr(kslot), 32, umma_idesc_bf16(128, 32, 0, 0), true);
             }
-            issue_qk(tile, slot_addr(kslot));
             if (tile == 0) ev(2, 14); else ev(2, 15);
           }
         }
@@ -376,10 +430,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp_idx == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
-template <int EMU, bool TRACE>
+template <int EMU, bool TRACE, int QSPLIT = 0>
 static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                        const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
-  auto kernel = attn_fwd_kernel<EMU, TRACE>;
+  auto kernel = attn_fwd_kernel<EMU, TRACE, QSPLIT>;
   static bool configured[64] = {false};
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));
@@ -433,11 +487,13 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
   p.lse = lse;
 
   debug_attach();
-  // MOVA_ATTN_VARIANT=v6 selects the experimental event-driven kernel of attn_v6.cu (see its header)
+  // MOVA_ATTN_VARIANT=v6 selects the experimental event-driven kernel of attn_v6.cu (see its header); v7 / v8 the
+  // sliced-QK schedules of this file (QSPLIT 1 / 2, see the kernel's header comment).  Default: v3.
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("MOVA_ATTN_VARIANT");
-    variant = (e != nullptr && e[0] == 'v' && e[1] == '6') ? 6 : 3;
+    variant = 3;
+    if (e != nullptr && e[0] == 'v' && e[1] >= '6' && e[1] <= '8' && e[2] == 0) variant = e[1] - '0';
   }
   // share of exponentials evaluated by polynomial (in 16ths of the pairs); MOVA_ATTN_EMU overrides for tuning
   static int emu = -1;
@@ -455,8 +511,11 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
     if (tbuf == nullptr) MV_CHECK_CUDA(cudaMalloc(&tbuf, 3 * 4096 * sizeof(unsigned long long)));
     MV_CHECK_CUDA(cudaMemsetAsync(tbuf, 0, 3 * 4096 * sizeof(unsigned long long), st));
     p.trace = tbuf;
-    int rc = (emu == 0) ? launch_attn<0, true>(grid, st, tmQ, tmK, tmV, tmO, p)
-                        : launch_attn<AT_DEFAULT_EMU, true>(grid, st, tmQ, tmK, tmV, tmO, p);
+    int rc;
+    if (variant == 7) rc = launch_attn<AT_DEFAULT_EMU, true, 1>(grid, st, tmQ, tmK, tmV, tmO, p);
+    else if (variant == 8) rc = launch_attn<AT_DEFAULT_EMU, true, 2>(grid, st, tmQ, tmK, tmV, tmO, p);
+    else rc = (emu == 0) ? launch_attn<0, true>(grid, st, tmQ, tmK, tmV, tmO, p)
+                         : launch_attn<AT_DEFAULT_EMU, true>(grid, st, tmQ, tmK, tmV, tmO, p);
     if (rc != 0) return rc;
     MV_CHECK_CUDA(cudaStreamSynchronize(st));
     static unsigned long long host[3 * 4096];
@@ -469,6 +528,8 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
     return 0;
   }
   if (variant == 6) return launch_attn_v6(grid, st, tmQ, tmK, tmV, tmO, p, emu);
+  if (variant == 7) return launch_attn<AT_DEFAULT_EMU, false, 1>(grid, st, tmQ, tmK, tmV, tmO, p);
+  if (variant == 8) return launch_attn<AT_DEFAULT_EMU, false, 2>(grid, st, tmQ, tmK, tmV, tmO, p);
   switch (emu) {
     case 0: return launch_attn<0, false>(grid, st, tmQ, tmK, tmV, tmO, p);
     case 2: return launch_attn<2, false>(grid, st, tmQ, tmK, tmV, tmO, p);
