@@ -35,6 +35,13 @@ SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
          c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     ),
+    "mova_b200_attn_fwd_ex": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+         c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    ),
+    "mova_b200_head_norms": (
+        c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mova_b200_lse_merge": (
         c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mova_b200_layernorm": (

@@ -57,6 +57,8 @@ constexpr uint32_t AT_TMEM_S = 0;    // + 128 * tile
 constexpr uint32_t AT_TMEM_O = 256;  // + 128 * tile
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 constexpr int AT_DEFAULT_EMU = 4;
+// BOUNDED: P = 2^(s - m) may grow to 2^64; the fp32 accumulators then stay below 2^64 * 2^18 keys * |v| << 2^127
+constexpr float AT_BOUND_SLACK = 64.0f;
 
 // EMU: how many of every 16 score pairs take the polynomial path (0 = all MUFU, 8 = half and half)
 // QSPLIT (experimental, MOVA_ATTN_VARIANT=v7 / v8; 0 = the shipped v3 schedule): Q.K^T of block j+1 is issued in
@@ -67,7 +69,13 @@ constexpr int AT_DEFAULT_EMU = 4;
 //                   QSPLIT 2: keys 0..31 after the first half of P.V(j), keys 32..63 after the second.
 // tcgen05.mma cost is linear in N (floor 128*N/256 cycles per K=16 step), so the tensor work is unchanged while the
 // dependent chain  P(j) ready -> S(j+1) ready  shrinks from P.V half + 512 cycles to P.V half + 256 (128) cycles.
-template <int EMU, bool TRACE, int QSPLIT>
+// BOUNDED (experimental, MOVA_ATTN_BOUNDED=1): the row maximum is only needed as a reference point that keeps
+// exp2(s - m) inside the fp32 range; softmax itself is invariant to it.  With |q_i| per query row and max_j |k_j| per
+// 128-key block supplied (mova_b200_head_norms), Cauchy-Schwarz gives an upper bound of every score of the block; while
+// that bound stays within 2^AT_BOUND_SLACK of the reference point already in use, the 128-element max reduction and
+// the rescale vote (about a quarter of the softmax time per block) are skipped.  When the bound is not good enough
+// the block takes the exact path below, so the result never depends on the inputs being "nice".
+template <int EMU, bool TRACE, int QSPLIT, bool BOUNDED>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -132,9 +140,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int tail = p.Skv - (n_kv - 1) * 128;  // valid keys of the last block, 1..128
       float m_used = -INFINITY;  // maximum (raw score units) the running O and l are expressed against
       float l = 0.f;
+      float qn_c = 0.f;                 // BOUNDED: |q_row| * scale * log2(e), rounded up
+      const float* kmax_row = nullptr;  // BOUNDED: max |k| of every key block of this (b, h)
+      if constexpr (BOUNDED) {
+        const int grow = row_base + tile * 128 + r;
+        if (grow < p.Sq) qn_c = p.qnorm[(static_cast<long long>(b) * p.Sq + grow) * p.H + h] * c * 1.001f;
+        kmax_row = p.kmax + (static_cast<long long>(b) * p.H + h) * n_kv;
+      }
 
 #pragma unroll 1
       for (int j = 0; j < n_kv; ++j) {
+        float kb = 0.f;
+        if constexpr (BOUNDED) kb = __ldg(kmax_row + j);  // in flight while this warp waits for S(j)
         mbar_wait(bar(AT_BAR_SFULL + tile), j & 1);
         tc_fence_after();
         if ((threadIdx.x & 127) == 0) ev(tile, 1);
@@ -154,6 +171,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 128; ++i)
             if (i >= tail) s[i] = 0xff800000u;  // -inf
         }
+        bool skip_max = false;
+        if constexpr (BOUNDED) {
+          // every score of this block is <= |q||k_max| (in exp2 units: qn_c * kb); if even that stays within the
+          // slack of the reference point in use, nothing can overflow and the exact maximum is not needed
+          if (j > 0) skip_max = __all_sync(0xffffffffu, fmaf(qn_c, kb, -m_used * c) <= AT_BOUND_SLACK);
+        }
+        if (!skip_max) {
         // 8 independent chains: the 3-input FMNMX has a long dependent-issue latency (4 chains cost ~420 cycles)
         float mx[8];
 #pragma unroll
@@ -187,6 +211,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_wait_st();
           }
         }
+        }  // !skip_max
         if ((threadIdx.x & 127) == 0) ev(tile, 3);
         const float neg = -m_used * c;
         const float2 c2 = make_float2(c, c);
@@ -430,10 +455,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp_idx == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
-template <int EMU, bool TRACE, int QSPLIT = 0>
+template <int EMU, bool TRACE, int QSPLIT = 0, bool BOUNDED = false>
 static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                        const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
-  auto kernel = attn_fwd_kernel<EMU, TRACE, QSPLIT>;
+  auto kernel = attn_fwd_kernel<EMU, TRACE, QSPLIT, BOUNDED>;
   static bool configured[64] = {false};
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));
@@ -452,7 +477,18 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
                                   const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs, int64_t o_ss,
                                   float* lse, int B, int Sq, int Skv, int H, int D, float softmax_scale,
                                   void* stream) {
+  return mova_b200_attn_fwd_ex(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, o_bs, o_ss, lse, B, Sq, Skv, H, D,
+                               softmax_scale, nullptr, nullptr, stream);
+}
+
+extern "C" int mova_b200_attn_fwd_ex(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs,
+                                     int64_t k_ss, const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs,
+                                     int64_t o_ss, float* lse, int B, int Sq, int Skv, int H, int D,
+                                     float softmax_scale, const float* q_norm, const float* k_block_max,
+                                     void* stream) {
   using namespace mv;
+  MV_REQUIRE((q_norm == nullptr) == (k_block_max == nullptr),
+             "mova_b200_attn_fwd_ex: q_norm and k_block_max must come together");
   MV_REQUIRE(q && k && v && o, "mova_b200_attn_fwd: null pointer");
   MV_REQUIRE(D == 128, "mova_b200_attn_fwd: head_dim %d unsupported (the MOVA towers and bridge use 128)", D);
   MV_REQUIRE(B >= 1 && H >= 1 && Sq >= 0 && Skv >= 1, "mova_b200_attn_fwd: bad shape B=%d Sq=%d Skv=%d H=%d", B, Sq,
@@ -485,6 +521,8 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.lse = lse;
+  p.qnorm = q_norm;
+  p.kmax = k_block_max;
 
   debug_attach();
   // MOVA_ATTN_VARIANT=v6 selects the experimental event-driven kernel of attn_v6.cu (see its header); v7 / v8 the
@@ -526,6 +564,11 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
       fclose(f);
     }
     return 0;
+  }
+  if (q_norm != nullptr && variant != 6) {  // bounded softmax (experimental): any of the schedules of this file
+    if (variant == 7) return launch_attn<AT_DEFAULT_EMU, false, 1, true>(grid, st, tmQ, tmK, tmV, tmO, p);
+    if (variant == 8) return launch_attn<AT_DEFAULT_EMU, false, 2, true>(grid, st, tmQ, tmK, tmV, tmO, p);
+    return launch_attn<AT_DEFAULT_EMU, false, 0, true>(grid, st, tmQ, tmK, tmV, tmO, p);
   }
   if (variant == 6) return launch_attn_v6(grid, st, tmQ, tmK, tmV, tmO, p, emu);
   if (variant == 7) return launch_attn<AT_DEFAULT_EMU, false, 1>(grid, st, tmQ, tmK, tmV, tmO, p);

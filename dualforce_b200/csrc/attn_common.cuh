@@ -12,6 +12,8 @@ struct AttnParams {
   float scale;       // softmax scale
   float scale_log2;  // scale * log2(e)
   float* lse;        // [B, H, Sq] or null
+  const float* qnorm;  // BOUNDED kernels: |q| per (b, query row, head), [B, Sq, H]
+  const float* kmax;   // BOUNDED kernels: max |k| per (b, head, 128-key block), [B, H, ceil(Skv/128)]
   unsigned long long* trace;  // diagnostics (MOVA_ATTN_TRACE): 3 regions of 4096 (clock << 8 | event) records
 };
 

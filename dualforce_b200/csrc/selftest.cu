@@ -244,8 +244,27 @@ static int test_attn(int argc, char** argv) {
   CK(cudaMalloc(&oref, static_cast<size_t>(B) * Sq * row * 4));
   CK(cudaMalloc(&lseref, static_cast<size_t>(B) * H * Sq * 4));
   const float scale = 1.0f / sqrtf(128.f) * 3.0f;  // sharper than 1/sqrt(D) so the softmax is not flat
-  CKMV(mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row, lse, B,
-                          Sq, Skv, H, D, scale, nullptr));
+  // MOVA_ATTN_BOUNDED=1: the bounded-softmax path (head norms + mova_b200_attn_fwd_ex), norms recomputed per call
+  const char* benv = getenv("MOVA_ATTN_BOUNDED");
+  const bool bounded = benv != nullptr && benv[0] == '1';
+  float *qn = nullptr, *km = nullptr;
+  if (bounded) {
+    CK(cudaMalloc(&qn, static_cast<size_t>(B) * Sq * H * 4));
+    CK(cudaMalloc(&km, static_cast<size_t>(B) * H * ((Skv + 127) / 128) * 4));
+    printf("  bounded softmax path\n");
+  }
+  auto run_attn = [&](float* lse_out) -> int {
+    if (!bounded)
+      return mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
+                                lse_out, B, Sq, Skv, H, D, scale, nullptr);
+    int rc = mova_b200_head_norms(q, q_bs, q_ss, B, Sq, H, D, qn, nullptr, nullptr);
+    if (rc != 0) return rc;
+    rc = mova_b200_head_norms(k, k_bs, k_ss, B, Skv, H, D, nullptr, km, nullptr);
+    if (rc != 0) return rc;
+    return mova_b200_attn_fwd_ex(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
+                                 lse_out, B, Sq, Skv, H, D, scale, qn, km, nullptr);
+  };
+  CKMV(run_attn(lse));
   CK(cudaDeviceSynchronize());
   bool ok = true;
   if (static_cast<double>(B) * H * Sq * Skv <= 4.0e9) {
@@ -271,13 +290,9 @@ static int test_attn(int argc, char** argv) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 2; ++i)
-      CKMV(mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
-                              nullptr, B, Sq, Skv, H, D, scale, nullptr));
+    for (int i = 0; i < 2; ++i) CKMV(run_attn(nullptr));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i)
-      CKMV(mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
-                              nullptr, B, Sq, Skv, H, D, scale, nullptr));
+    for (int i = 0; i < iters; ++i) CKMV(run_attn(nullptr));
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms;
