@@ -307,6 +307,8 @@ def run_b200_arm(args):
         cfg["audio_layers"] = args.audio_layers
     if args.frames is not None:
         cfg["grid_size"] = ((args.frames - 1) // 4 + 1, 22, 40)
+    if args.res == "720p":  # BASELINE.json configs[3]: 720x1280 -> token grid (f, 45, 80), L_v = 176400 at 193 frames
+        cfg["grid_size"] = (cfg["grid_size"][0], 45, 80)
     full = (cfg == FULL_360P)
 
     step_api_error = None
@@ -502,7 +504,7 @@ def run_b200_arm(args):
             "config": {"workload": ("MOVA-360p full dual-tower DiT denoising step: 2 CFG forwards x (40 video blocks "
                                     "5120/40h/ffn13824 + 30 audio blocks 1536/12h/ffn8960 + 30 bidirectional bridge "
                                     "layers), L_v=43120 (352x640x193f), L_a=403, 512 text tokens, random init")
-                       if full else f"REDUCED (not the headline config): {cfg}",
+                       if full else f"NOT the headline config (debug / BASELINE configs[3]): {cfg}",
                        "cp_size": world, "parallelism": f"cp{world}" if world > 1 else "single GPU",
                        "launch_mode": "cuda graph replay" if use_graph else "eager",
                        "l2_policy": "inputs+weights (~36 GB touched per forward) far exceed the 126 MB L2; no flush needed",
@@ -587,6 +589,8 @@ def main():
     ap.add_argument("--video-layers", type=int, default=None, help="debug: reduced depth (marks the line REDUCED)")
     ap.add_argument("--audio-layers", type=int, default=None)
     ap.add_argument("--frames", type=int, default=None, help="debug: clip length in frames (default 193)")
+    ap.add_argument("--res", choices=["360p", "720p"], default="360p",
+                    help="720p = BASELINE.json configs[3] (L_v = 176400; meant for --gpus 8); marks the line REDUCED/other")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=None,
                     help="1: replay the forward as a CUDA graph, 0: eager launches (default)")
