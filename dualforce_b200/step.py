@@ -39,7 +39,7 @@ from . import ops, rope
 from .modules import DiTBlock
 
 __all__ = ["Head", "WanModel", "WanAudioModel", "inference_single_step", "embed_time", "embed_text", "patchify",
-           "head_unpatchify", "guided_update", "clear_step_caches"]
+           "head_unpatchify", "guided_update", "denoising_loop", "clear_step_caches"]
 
 _STATIC_FLAG = "_mova_b200_static"  # set on context embeddings whose per-layer k / v may be memoised
 
@@ -398,6 +398,47 @@ def guided_update(noise_pred_posi: torch.Tensor, noise_pred_nega: Optional[torch
     if sample.dtype != torch.float32:
         raise TypeError(f"guided_update: latents are kept in fp32 by the pipeline (pipeline_mova.py:378-399), got {sample.dtype}")
     return ops.cfg_euler_step(posi, nega, sample, float(cfg_scale), dsigma, out=out)
+
+
+@torch.no_grad()
+def denoising_loop(pipe, latents: torch.Tensor, condition: torch.Tensor, audio_latents: torch.Tensor,
+                   prompt_embeds: torch.Tensor, negative_prompt_embeds: Optional[torch.Tensor], paired_timesteps,
+                   timestep_to_sigma, video_fps: float, cfg_scale: float = 5.0, cp_mesh=None, pick_visual_dit=None,
+                   final_sigma: float = 0.0):
+    """The diffusion loop of ``MOVA.__call__`` (pipeline_mova.py:405-487) on the B200 step: per scheduler iteration
+    two ``inference_single_step`` calls (one when ``cfg_scale == 1``), then CFG + ``step_from_to`` fused in
+    ``guided_update``.  ``latents [1, 16, F, H, W]`` / ``audio_latents [1, 128, L_a]`` are the fp32 noise tensors,
+    ``condition [1, 20, F, H, W]`` the mask + first-frame channels (:416); ``paired_timesteps`` is the ``[N, 2]`` tensor
+    of ``scheduler.get_pairs()`` and ``timestep_to_sigma`` the reference scheduler's own lookup (:198-211) -- the
+    scheduler stays the reference's.  ``pick_visual_dit(timestep_value) -> model`` implements the high / low-noise
+    expert switch (:407-413); default: ``pipe.video_dit``.  Returns the final fp32 ``(latents, audio_latents)``.
+
+    The model input ``cat([latents, condition], dim=1)`` (:416) is one persistent buffer whose first 16 channels are
+    updated in place by the fused kernel, so no concatenation copy runs per step."""
+    dev = latents.device
+    n_lat = latents.shape[1]
+    model_input = torch.cat([latents.float(), condition.float()], dim=1).contiguous()  # once per video
+    lat_view = model_input[:, :n_lat]
+    audio = audio_latents.float().contiguous().clone()
+    total = paired_timesteps.shape[0]
+    for idx in range(total):
+        t_v, t_a = paired_timesteps[idx]
+        visual_dit = pick_visual_dit(float(t_v)) if pick_visual_dit is not None else pipe.video_dit
+        ts_v = t_v.reshape(1).to(device=dev, dtype=torch.float32)
+        ts_a = t_a.reshape(1).to(device=dev, dtype=torch.float32)
+        kw = dict(visual_dit=visual_dit, visual_latents=model_input, audio_latents=audio, timestep=ts_v,
+                  audio_timestep=ts_a, video_fps=video_fps, cp_mesh=cp_mesh)
+        pos_v, pos_a = pipe.inference_single_step(context=prompt_embeds, **kw)
+        neg_v = neg_a = None
+        if cfg_scale != 1.0:
+            neg_v, neg_a = pipe.inference_single_step(context=negative_prompt_embeds, **kw)
+        nxt = paired_timesteps[idx + 1] if idx + 1 < total else None
+        sig_v, sig_a = timestep_to_sigma(t_v), timestep_to_sigma(t_a)
+        sig_v_to = timestep_to_sigma(nxt[0]) if nxt is not None else final_sigma
+        sig_a_to = timestep_to_sigma(nxt[1]) if nxt is not None else final_sigma
+        guided_update(pos_v, neg_v, lat_view, cfg_scale, sig_v, sig_v_to, out=lat_view)
+        guided_update(pos_a, neg_a, audio, cfg_scale, sig_a, sig_a_to, out=audio)
+    return lat_view.clone(), audio
 
 
 def bind(pipe) -> None:

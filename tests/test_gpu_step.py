@@ -196,6 +196,32 @@ def test_step_at_mova_widths_vs_oracle():
     assert_close(a, ra, "360p-width step audio", ratio=3e-2, fro=1.5e-2)
 
 
+def test_end_of_schedule_latent_cosine():
+    """north_star's second tolerance -- end-of-schedule latent cosine similarity: 4 scheduler iterations x 2 CFG
+    forwards of the reduced-depth dual tower through the denoising loop (persistent model-input buffer, memoised
+    prompt work, fused CFG + Euler update) against the oracle's restatement of MOVA.__call__'s loop (fp32)."""
+    from dualforce_b200 import step
+    from util import metrics
+
+    cfg, Pv, Pa, Pb, inp, gold = _step_case()
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
+    g = torch.Generator().manual_seed(12)
+    f, h, w = cfg["grid_size"]
+    latents = torch.randn(1, 16, f, 2 * h, 2 * w, generator=g)
+    condition = torch.randn(1, 20, f, 2 * h, 2 * w, generator=g)
+    audio = torch.randn(1, cfg["audio_in_dim"], cfg["audio_len"], generator=g)
+    pos = inp["context"].to(torch.bfloat16)
+    neg = (torch.randn(pos.shape, generator=g) * 0.5).to(torch.bfloat16)
+    sched = O.PairScheduler(num_inference_steps=4)
+    ref_v, ref_a = O.denoising_loop(Pv, Pa, Pb, cfg, latents, condition, audio, pos.float(), neg.float(), sched, 5.0)
+    got_v, got_a = step.denoising_loop(pipe, latents.cuda(), condition.cuda(), audio.cuda(), pos.cuda(), neg.cuda(),
+                                       sched.get_pairs(), sched.timestep_to_sigma, cfg["video_fps"], cfg_scale=5.0)
+    mv, ma = metrics(got_v, ref_v), metrics(got_a, ref_a)
+    assert mv["finite"] and ma["finite"]
+    assert mv["cos"] >= 0.999 and ma["cos"] >= 0.999, (mv, ma)
+    assert mv["rel_fro"] <= 3e-2 and ma["rel_fro"] <= 3e-2, (mv, ma)
+
+
 # ------------------------------------------------------------------------------------------------ context parallel
 def _free_port():
     with socket.socket() as s:

@@ -299,3 +299,36 @@ def test_guided_update_host_logic(emu):
     assert out.data_ptr() == buf.data_ptr() and (buf[:, :16] - O.guided_update(posi, None, lat, 1.0, 0.9, 0.0)).abs().max() <= 1e-6
     with pytest.raises(TypeError):
         step.guided_update(posi, nega, lat.to(torch.bfloat16), 5.0, 0.9, 0.85)
+
+
+def test_end_of_schedule_latents_host_logic(emu, step_case):
+    """north_star's second tolerance: end-of-schedule latent cosine similarity.  4 scheduler iterations x 2 CFG
+    forwards of the tiny dual tower through the product's denoising loop (persistent model-input buffer, memoised
+    prompt work, fused CFG + Euler update) against the oracle's restatement of MOVA.__call__'s loop."""
+    from dualforce_b200 import step
+    from util import metrics
+
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    g = torch.Generator().manual_seed(12)
+    f, h, w = cfg["grid_size"]
+    latents = torch.randn(1, 16, f, 2 * h, 2 * w, generator=g)
+    condition = torch.randn(1, 20, f, 2 * h, 2 * w, generator=g)
+    audio = torch.randn(1, cfg["audio_in_dim"], cfg["audio_len"], generator=g)
+    pos = inp["context"].to(torch.bfloat16)
+    neg = (torch.randn(pos.shape, generator=g) * 0.5).to(torch.bfloat16)
+    sched = O.PairScheduler(num_inference_steps=4)
+    assert torch.all(sched.sigmas[:-1] > sched.sigmas[1:]) and abs(float(sched.sigmas[0]) - 1.0) < 1e-6
+    ref_v, ref_a = O.denoising_loop(Pv, Pa, Pb, cfg, latents, condition, audio, pos.float(), neg.float(), sched, 5.0)
+    got_v, got_a = step.denoising_loop(pipe, latents, condition, audio, pos, neg, sched.get_pairs(),
+                                       sched.timestep_to_sigma, cfg["video_fps"], cfg_scale=5.0)
+    mv, ma = metrics(got_v, ref_v), metrics(got_a, ref_a)
+    assert mv["finite"] and ma["finite"]
+    assert mv["cos"] >= 0.999 and ma["cos"] >= 0.999, (mv, ma)
+    assert mv["rel_fro"] <= 3e-2 and ma["rel_fro"] <= 3e-2, (mv, ma)
+    assert (ref_v - latents).abs().max() > 0.5  # the schedule moved the latents
+    # the caller's tensors are untouched; prompt work ran once per prompt, not once per step
+    assert emu["patchify"] == 4 * 2 * 2 and emu["cfg_euler_step"] == 4 * 2
+    n_blocks = cfg["visual_layers"] + cfg["audio_layers"]
+    per_forward = 17 * n_blocks + 14 * min(cfg["visual_layers"], cfg["audio_layers"])
+    assert emu["linear"] + emu["layernorm"] + emu["rmsnorm_rope_"] + emu["attention"] + emu["add_to_f32"] < 8 * (per_forward + 12)

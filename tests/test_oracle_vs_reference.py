@@ -120,3 +120,58 @@ def test_step_matches_reference(seed, grid, audio_len, timestep):
         ref = torch.from_numpy(arrays[key])
         assert got.shape == ref.shape
         assert (got - ref).abs().max() <= 5e-5 * max(ref.abs().max().item(), 1.0)
+
+
+def _load_reference_schedulers():
+    """flow_match.py / flow_match_pair.py with mmengine's registry and diffusers' SchedulerMixin stubbed (neither is
+    installed here; both only decorate / subclass, no arithmetic)."""
+    import importlib
+    import sys
+    import types
+
+    ref_loader.load()
+    if "mova.registry" not in sys.modules or not hasattr(sys.modules["mova.registry"], "DIFFUSION_SCHEDULERS"):
+        reg = types.ModuleType("mova.registry")
+
+        class _Registry:
+            def register_module(self, *a, **k):
+                return lambda cls: cls
+
+        reg.DIFFUSION_SCHEDULERS = _Registry()
+        sys.modules["mova.registry"] = reg
+    if "diffusers.schedulers.scheduling_utils" not in sys.modules:
+        sch = types.ModuleType("diffusers.schedulers")
+        su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+        su.SchedulerMixin = type("SchedulerMixin", (), {})
+        sch.scheduling_utils = su
+        sys.modules["diffusers.schedulers"] = sch
+        sys.modules["diffusers.schedulers.scheduling_utils"] = su
+    pkg = "mova.diffusion.schedulers"
+    if pkg not in sys.modules:
+        m = types.ModuleType(pkg)
+        m.__path__ = [__import__("os").path.join(ref_loader.REFERENCE_ROOT, "mova", "diffusion", "schedulers")]
+        sys.modules[pkg] = m
+    return importlib.import_module(pkg + ".flow_match_pair")
+
+
+@pytest.mark.parametrize("steps", [4, 50])
+def test_scheduler_tables_and_update_match_reference(steps):
+    """The oracle's PairScheduler / guided_update against the reference's FlowMatchPairScheduler (MOVA config: shift 5,
+    extra_one_step): inference tables, the train-table sigma lookup and step_from_to."""
+    fmp = _load_reference_schedulers()
+    ref = fmp.FlowMatchPairScheduler(num_inference_steps=steps, num_train_timesteps=1000, shift=5.0, extra_one_step=True)
+    mine = O.PairScheduler(num_inference_steps=steps)
+    assert torch.equal(ref.get_pairs(), mine.get_pairs())
+    assert torch.equal(ref.train_sigmas, mine.train_sigmas)
+    pairs = ref.get_pairs()
+    g = torch.Generator().manual_seed(1)
+    sample, posi, nega = (torch.randn(2, 3, 5, generator=g) for _ in range(3))
+    for i in range(steps):
+        t = pairs[i, 0]
+        nxt = pairs[i + 1, 0] if i + 1 < steps else None
+        assert float(ref.timestep_to_sigma(t)) == float(mine.timestep_to_sigma(t))
+        noise = nega + 5.0 * (posi - nega)
+        want = ref.step_from_to(noise, t, nxt, sample)
+        got = O.guided_update(posi, nega, sample, 5.0, float(mine.timestep_to_sigma(t)),
+                              float(mine.timestep_to_sigma(nxt)) if nxt is not None else 0.0)
+        assert (want - got).abs().max() <= 1e-6
