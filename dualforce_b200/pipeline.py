@@ -11,6 +11,7 @@ merge for the v2a bridge -- and returns the same full-length tensors as cp=1.
 from __future__ import annotations
 
 import contextlib
+import os
 import types
 from typing import Optional, Sequence, Tuple
 
@@ -29,13 +30,20 @@ __all__ = ["forward_dual_tower_dit", "install", "swap_modules", "CPRuntime", "Gr
 class CPRuntime:
     """Process-group handle + the communication stream the all-to-alls are queued on."""
 
-    def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: int = 2):
+    def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: Optional[int] = None,
+                 attn_streams: Optional[int] = None):
         self.group, self.rank, self.size, self.device = group, rank, size, device
-        self.head_groups = head_groups
+        # Tuning knobs (defaults = the measured round-1 configuration: 2 head groups, attention on the main stream).
+        # MOVA_CP_HEAD_GROUPS=5 with MOVA_CP_ATTN_STREAMS=2 is the experiment for cp = 8, where 5 heads per rank do not
+        # split in two and the all-to-alls are fully exposed: one head per group, and the per-group attention kernels
+        # spread over side streams so that their partial last waves overlap instead of serialising (unmeasured).
+        self.head_groups = int(os.environ.get("MOVA_CP_HEAD_GROUPS", "2")) if head_groups is None else head_groups
+        n_attn = int(os.environ.get("MOVA_CP_ATTN_STREAMS", "0")) if attn_streams is None else attn_streams
         self.comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self.attn_streams = [torch.cuda.Stream(device=device) for _ in range(n_attn)] if device.type == "cuda" else []
 
     @classmethod
-    def from_mesh(cls, cp_mesh, device: torch.device, head_groups: int = 2) -> "CPRuntime":
+    def from_mesh(cls, cp_mesh, device: torch.device, head_groups: Optional[int] = None) -> "CPRuntime":
         key = (id(cp_mesh), str(device), head_groups)
         rt = _RUNTIMES.get(key)
         if rt is None:
@@ -118,12 +126,22 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
             cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
             in_done.append(record(comm))
     outs, out_done = [], []
+    side = rt.attn_streams if comm is not None else []
+    if side:  # attention outputs allocated up front on the compute stream, like recv / back
+        outs = [torch.empty(1, L, wd, dtype=torch.bfloat16, device=h.device) for _ in range(G)]
     for g in range(G):
-        wait(main, in_done[g])
         qkv = recv[g].unsqueeze(0)
-        o = ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg)  # [1, L, wd]
-        outs.append(o)
-        att = record(main)
+        if side:
+            st = side[g % len(side)]
+            with torch.cuda.stream(st):
+                wait(st, in_done[g])
+                o = ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=outs[g])
+                att = record(st)
+        else:
+            wait(main, in_done[g])
+            o = ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg)  # [1, L, wd]
+            outs.append(o)
+            att = record(main)
         with on_comm():
             wait(comm, att)
             cpmod.gather_heads(o[0], rows_per_rank, rt.rank, rt.group, out=back[g])
