@@ -24,6 +24,8 @@ cd ../..
 MOVA_ATTN_VARIANT=v8 MOVA_ATTN_BOUNDED=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_v8b.json 2> gpurun_out/r2_bench_v8b.err
 python bench.py --steps 2 --warmup 3 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 
+MOVA_V2A_SPLITS=5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_v2a_split5.json 2> gpurun_out/r2_bench_v2a_split5.err
+
 # 4. (gpurun --gpus 8) context parallel: default vs one-head groups with overlapped attention launches
 #   torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 bench.py --gpus 8 --steps 3 --warmup 3
 #   MOVA_CP_HEAD_GROUPS=5 MOVA_CP_ATTN_STREAMS=2 torchrun ... (same)

@@ -18,6 +18,7 @@ Fusion plan per DiTBlock (17 launches instead of ~60 library kernels):
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -69,6 +70,15 @@ def merged_linear(layer: nn.Module) -> nn.Linear:
             out.bias = nn.Parameter(base.bias.data.clone(), requires_grad=False)
         return out
     raise TypeError(f"expected nn.Linear or a LoRA-wrapped linear, got {type(layer).__module__}.{type(layer).__name__}")
+
+
+def _kv_splits(n_queries: int, n_keys: int) -> int:
+    """Split-KV factor for occupancy-bound cross-attention (opt-in: ``MOVA_V2A_SPLITS=<n>``, unmeasured; default 1).
+    Only for few queries against many keys, and only when the keys divide evenly (43 120 = 5 x 8624 = 7 x 6160)."""
+    want = int(os.environ.get("MOVA_V2A_SPLITS", "1"))
+    if want <= 1 or n_queries > 1024 or n_keys < 8192 or n_keys % want:
+        return 1
+    return want
 
 
 class _Packed:
@@ -399,7 +409,22 @@ class ConditionalCrossAttention(nn.Module):
     def attend(self, x, y, x_freqs=None, y_freqs=None):
         q = self.project_q(x, x_freqs)
         k, v = self.project_kv(y, y_freqs)
+        splits = _kv_splits(q.shape[1], k.shape[1]) if q.shape[0] == 1 else 1
+        if splits > 1:
+            return self._attend_split_kv(q, k, v, splits)
         return self.attn(q, k, v)
+
+    def _attend_split_kv(self, q, k, v, splits: int):
+        """Few queries, many keys (v2a: 403 audio queries x 43 120 video keys x 12 heads = 24 CTAs on 148 SMs): cut the
+        keys in ``splits`` equal chunks, run them as the BATCH dimension of one attention launch (24 x splits CTAs, all
+        resident at once), and merge the partial results exactly with their log-sum-exps."""
+        _, Sq, HD = q.shape
+        chunk = k.shape[1] // splits
+        kc = k[0].unflatten(0, (splits, chunk))  # strided view [splits, chunk, HD] of the fused k|v buffer
+        vc = v[0].unflatten(0, (splits, chunk))
+        qe = q.expand(splits, Sq, HD).contiguous()  # the kernel's tensor map wants a real batch stride (6 MB at 360p)
+        o, lse = ops.attention(qe, kc, vc, self.num_heads, return_lse=True)
+        return ops.lse_merge(o, lse, self.num_heads).unsqueeze(0)
 
     def forward(self, x: torch.Tensor, y: torch.Tensor, x_freqs=None, y_freqs=None) -> torch.Tensor:
         return ops.linear(self.attend(x, y, x_freqs, y_freqs), self.o.weight, self.o.bias)

@@ -116,3 +116,38 @@ def test_bounded_attention_through_ops_both_paths():
         assert (lse.cpu() - ref_lse).abs().max() <= 2e-3 * max(1.0, ref_lse.abs().max().item())
         plain = B.ops.attention(qs.cuda(), k.cuda(), v.cuda(), H, bounded=False)
         assert_close(got, plain.float().cpu(), f"bounded vs plain kernel, q x{qscale}", ratio=1.5e-2, fro=6e-3)
+
+
+def test_split_kv_bridge_attention_on_device(monkeypatch):
+    """MOVA_V2A_SPLITS=5 at the real v2a shape (403 audio queries, 43 120 video keys, 12 heads): same result as the
+    single-launch path, and faster (24 -> 120 CTAs)."""
+    import torch
+
+    import dualforce_b200 as B
+    from util import assert_close
+
+    B._lib.require_device(0)
+    g = torch.Generator().manual_seed(2)
+    cca = B.ConditionalCrossAttention(1536, 5120, 12)
+    for prm in cca.parameters():
+        prm.data = torch.randn(prm.shape, generator=g) * (0.02 if prm.dim() > 1 else 0.1)
+    cca.to("cuda", torch.bfloat16)
+    x = torch.randn(1, 403, 1536, generator=g).to(torch.bfloat16).cuda()
+    y = torch.randn(1, 43120, 5120, generator=g).to(torch.bfloat16).cuda()
+
+    def timed(n):
+        monkeypatch.setenv("MOVA_V2A_SPLITS", str(n))
+        out = cca.attend(x, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            cca.attend(x, y)
+        e1.record()
+        e1.synchronize()
+        return out, e0.elapsed_time(e1) / 5
+
+    plain, t1 = timed(1)
+    split, t5 = timed(5)
+    assert_close(split, plain.float().cpu(), "split-KV vs unsplit", ratio=1e-2, fro=6e-3)
+    assert t5 < t1, f"split {t5:.3f} ms vs unsplit {t1:.3f} ms (projections included in both)"

@@ -332,3 +332,27 @@ def test_end_of_schedule_latents_host_logic(emu, step_case):
     n_blocks = cfg["visual_layers"] + cfg["audio_layers"]
     per_forward = 17 * n_blocks + 14 * min(cfg["visual_layers"], cfg["audio_layers"])
     assert emu["linear"] + emu["layernorm"] + emu["rmsnorm_rope_"] + emu["attention"] + emu["add_to_f32"] < 8 * (per_forward + 12)
+
+
+def test_split_kv_bridge_attention_host_logic(emu, monkeypatch):
+    """MOVA_V2A_SPLITS: keys cut in equal chunks run as the batch dimension of one launch + exact LSE merge."""
+    import dualforce_b200 as B
+
+    monkeypatch.setenv("MOVA_V2A_SPLITS", "5")
+    g = torch.Generator().manual_seed(2)
+    dim, kv_dim, H = 256, 384, 2
+    cca = B.ConditionalCrossAttention(dim, kv_dim, H).to(torch.bfloat16)
+    for prm in cca.parameters():
+        prm.data = (torch.randn(prm.shape, generator=g) * (0.05 if prm.dim() > 1 else 0.1)).to(torch.bfloat16)
+    x = torch.randn(1, 7, dim, generator=g).to(torch.bfloat16)
+    y = torch.randn(1, 8200 - 8200 % 5, kv_dim, generator=g).to(torch.bfloat16)  # 8200 keys: 5 chunks of 1640
+    split = cca(x, y)
+    assert emu["lse_merge"] == 1 and emu["attention"] == 1
+    monkeypatch.setenv("MOVA_V2A_SPLITS", "1")
+    plain = cca(x, y)
+    assert emu["lse_merge"] == 1 and emu["attention"] == 2
+    assert_close(split, plain.float(), "split-KV vs unsplit", ratio=1e-2, fro=6e-3)
+    # not applicable (many queries, or keys not divisible): falls back silently
+    monkeypatch.setenv("MOVA_V2A_SPLITS", "7")
+    cca(x, y)
+    assert emu["lse_merge"] == 1
