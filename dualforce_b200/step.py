@@ -242,10 +242,6 @@ class WanAudioModel(_Tower):
 # ----------------------------------------------------------------------------------------------------------------
 # the pieces of the step (duck-typed on the model: work on the twins above and on reference towers after install)
 # ----------------------------------------------------------------------------------------------------------------
-def _is_audio(model) -> bool:
-    return isinstance(model.patch_embedding, nn.Conv1d)
-
-
 def embed_time(model, timestep: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """``t = time_embedding(sinusoidal(timestep))``, ``t_mod = time_projection(t)`` (pipeline_mova.py:544-555):
     fp32 math, results rounded to the model dtype.  Returns ``(t [1, dim], t_mod [1, 6, dim])`` in bf16."""

@@ -4,7 +4,6 @@ product's own `_forward_eager` CP branch, weight permutation cache, sharded a2v 
 replicated audio tower, and the step wrapper's sequence-sharded head + narrow all-gather."""
 import os
 import socket
-import types
 
 import pytest
 import torch
@@ -43,7 +42,6 @@ def _worker(rank, world, port, grid, results):
     try:
         import dualforce_b200.ops as real_ops
         import emulated_ops
-        from test_oracle_step_golden import load_step_case
         from util import bf16_round, build_step_towers, metrics
 
         for name, fn in emulated_ops.ENTRY_POINTS.items():
