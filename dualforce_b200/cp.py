@@ -184,3 +184,55 @@ def ulysses_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_hea
     dist.all_to_all_single(recv, send, group=group)
     # recv[src] = this rank's tokens, heads of rank src -> [B, Sl, P*Hc*D]
     return recv.permute(1, 2, 0, 3).reshape(B, Sl, HD)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Forward-only twins of the reference's sequence-parallel helpers (mova/distributed/functional.py:55-121), for callers
+# that keep the reference loop (pad-and-strip semantics, same return tuples).  Pure index / byte plumbing: bit-exact
+# with the reference.  ``forward_dual_tower_dit`` itself does not use them (it shards ragged, never pads -- see the
+# module docstring); the autograd halves (_AllGather / _AllGatherAvg.backward) belong to training and are not built.
+# ----------------------------------------------------------------------------------------------------------------
+def _sp_split_tensor(x: torch.Tensor, *, sp_size: int, sp_rank: int, dim: int = 1):
+    """functional.py:55-73: ``torch.chunk`` along ``dim``, zero chunk for surplus ranks, zero-pad a short chunk.
+    Returns ``(chunk, chunk_len, pad_len, total_len)``."""
+    total_len = x.shape[dim]
+    chunks = torch.chunk(x, sp_size, dim=dim)
+    chunk_len = chunks[0].shape[dim]
+    if sp_rank < len(chunks):
+        chunk = chunks[sp_rank]
+    else:
+        shape = list(x.shape)
+        shape[dim] = chunk_len
+        chunk = x.new_zeros(shape)
+    if chunk.shape[dim] < chunk_len:
+        shape = list(chunk.shape)
+        shape[dim] = chunk_len - chunk.shape[dim]
+        chunk = torch.cat([chunk, x.new_zeros(shape)], dim=dim)
+    return chunk, chunk_len, chunk_len * sp_size - total_len, total_len
+
+
+def _sp_split_tensor_dim_0(x: torch.Tensor, *, sp_size: int, sp_rank: int):
+    """functional.py:76-96 (the RoPE tables are split along dim 0)."""
+    return _sp_split_tensor(x, sp_size=sp_size, sp_rank=sp_rank, dim=0)
+
+
+def _sp_all_gather(x_local: torch.Tensor, *, sp_group: Optional[dist.ProcessGroup], pad_len: int) -> torch.Tensor:
+    """functional.py:99-104 forward: all-gather the equal-length chunks, concatenate along dim 1, strip the padding."""
+    parts = [torch.empty_like(x_local) for _ in range(dist.get_world_size(group=sp_group))]
+    dist.all_gather(parts, x_local.contiguous(), group=sp_group)
+    gathered = torch.cat(parts, dim=1)
+    return gathered[:, :-pad_len] if pad_len > 0 else gathered
+
+
+def _sp_all_gather_avg(x_local: torch.Tensor, *, sp_group: Optional[dist.ProcessGroup], pad_len: int) -> torch.Tensor:
+    """functional.py:107-112 forward (the AVG only concerns the backward reduce-scatter): same as ``_sp_all_gather``."""
+    return _sp_all_gather(x_local, sp_group=sp_group, pad_len=pad_len)
+
+
+def _sp_select_rank(x_global: torch.Tensor, *, sp_size: int, sp_rank: int, chunk_len: int, pad_len: int):
+    """functional.py:115-121: this rank's (padded) slice of a full-length tensor."""
+    total_padded = chunk_len * sp_size
+    if pad_len > 0 and x_global.shape[1] != total_padded:
+        x_global = torch.nn.functional.pad(x_global, (0, 0, 0, total_padded - x_global.shape[1]))
+    start = sp_rank * chunk_len
+    return x_global[:, start:start + chunk_len]

@@ -70,7 +70,14 @@ def _worker(rank, world, port, grid, results):
         full_v, full_a = pipe.forward_dual_tower_dit(
             vis, tok, tok_a, step.embed_text(vis, ctx), step.embed_text(aud, ctx), t_mod, ta_mod,
             step.token_freqs(vis, g, "cpu"), step.token_freqs(aud, (f,), "cpu"), g, cfg["video_fps"], cp_mesh=mesh)
-        results[rank] = dict(
+        # the reference-style pad / gather helpers (functional.py:55-112 twins) across the two ranks
+        from dualforce_b200 import cp
+
+        tab = torch.arange(1 * 7 * 4, dtype=torch.float32).reshape(1, 7, 4)  # 7 rows over 2 ranks: 4 + (3 + 1 pad)
+        chunk, chunk_len, pad_len, total = cp._sp_split_tensor(tab, sp_size=world, sp_rank=rank)
+        sp_ok = bool(torch.equal(cp._sp_all_gather_avg(chunk, sp_group=None, pad_len=pad_len), tab)
+                     and (chunk_len, pad_len, total) == (4, 1, 7))
+        results[rank] = dict(sp_ok=sp_ok, 
             cp_vs_oracle_v=metrics(v2, rv), cp_vs_oracle_a=metrics(a2, ra), cp_vs_cp1_v=metrics(v2, v1.float()),
             cp_vs_cp1_a=metrics(a2, a1.float()), shapes=(tuple(v2.shape), tuple(a2.shape), tuple(full_v.shape)),
             calls=calls, v2=v2.float(), a2=a2.float())
@@ -96,5 +103,6 @@ def test_step_context_parallel_world2(grid):
             assert m["ratio"] <= 2e-2 and m["rel_fro"] <= 6e-3, (rank, key, m)
         # v2a merges partial attentions: one lse_merge per bridge layer
         assert r["calls"]["lse_merge"] == 2
+        assert r["sp_ok"]
     # every rank ends with the same full-length outputs
     assert torch.equal(results[0]["v2"], results[1]["v2"]) and torch.equal(results[0]["a2"], results[1]["a2"])

@@ -148,3 +148,33 @@ def test_from_reference_shares_parameters_and_counts_like_replace_attention():
     assert sorted(br.state_dict().keys()) == sorted(ref_bridge.state_dict().keys())
     assert br.audio_to_video_conditioners["1"].inner.k.weight is ref_bridge.audio_to_video_conditioners["1"].inner.k.weight
     assert br.apply_cross_rope and br.should_interact(1, "v2a")
+
+
+def test_sp_helper_twins_match_reference_golden(meta):
+    """dualforce_b200.cp._sp_* (forward-only twins of mova/distributed/functional.py) against the reference's own
+    outputs in the golden file: pure index work, bit-exact."""
+    import numpy as np
+
+    import mova_oracle as O
+    from dualforce_b200 import cp
+
+    gold = np.load(os.path.join(GOLDEN, "tiny_dual_tower.npz"))
+    cfg = dict(meta["cfg"], grid_size=tuple(meta["cfg"]["grid_size"]))
+    _, _, _, inp = O.make_case(cfg, meta["seed"])
+    x = inp["audio_x"]  # [1, 21, 128]: 4 ranks -> chunks of 6, last one short, 3 pad rows
+    chunks = []
+    for r in range(4):
+        c, chunk_len, pad_len, total = cp._sp_split_tensor(x, sp_size=4, sp_rank=r)
+        assert torch.equal(c, torch.from_numpy(gold[f"sp_split_r{r}"]))
+        assert (chunk_len, pad_len, total) == (6, 3, 21)
+        chunks.append(c)
+    full = torch.cat(chunks, dim=1)[:, :-3]
+    assert torch.equal(full, x)
+    # surplus rank (more ranks than chunks) gets zeros; dim-0 variant on a table
+    c, chunk_len, pad_len, total = cp._sp_split_tensor(x[:, :3], sp_size=4, sp_rank=3)
+    assert chunk_len == 1 and pad_len == 1 and torch.equal(c, torch.zeros(1, 1, 128))
+    tab = torch.arange(21 * 4, dtype=torch.float32).reshape(21, 1, 4)
+    c0, cl, pl, tot = cp._sp_split_tensor_dim_0(tab, sp_size=4, sp_rank=3)
+    assert (cl, pl, tot) == (6, 3, 21) and torch.equal(c0[:3], tab[18:]) and torch.equal(c0[3:], torch.zeros(3, 1, 4))
+    sel = cp._sp_select_rank(x, sp_size=4, sp_rank=3, chunk_len=6, pad_len=3)
+    assert torch.equal(sel, chunks[3])
