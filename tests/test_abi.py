@@ -47,3 +47,32 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "mova_oracle" not in src and "ref_loader" not in src, f"{fn} references the test oracle"
+            assert "emulated_ops" not in src, f"{fn} references the tests' kernel emulation"
+
+
+def test_every_ops_entry_point_rejects_cpu_tensors():
+    """Every kernel front end of dualforce_b200.ops (old and new) raises on CPU tensors instead of computing anything."""
+    import torch
+
+    import dualforce_b200 as B
+
+    bf = torch.zeros(8, 128, dtype=torch.bfloat16)
+    f32 = torch.zeros(128, dtype=torch.float32)
+    calls = [
+        lambda: B.ops.layernorm(bf, 1e-6),
+        lambda: B.ops.rmsnorm_rope_(bf, bf[0], 1e-6),
+        lambda: B.ops.lse_merge(bf[None], torch.zeros(1, 1, 8), 1),
+        lambda: B.ops.add_to_f32(bf),
+        lambda: B.ops.patchify(torch.zeros(4, 2, 2, 2), (1, 2, 2)),
+        lambda: B.ops.unpatchify(bf, (8,), (1,), 128),
+        lambda: B.ops.sinusoidal_embedding(256, torch.zeros(1)),
+        lambda: B.ops.gemv_f32(f32, bf),
+        lambda: B.ops.cfg_euler_step(bf, None, torch.zeros(8, 128), 1.0, -0.1),
+        lambda: B.ops.head_norms(bf[None], 1, rows=True),
+    ]
+    for i, call in enumerate(calls):
+        with pytest.raises(B.MovaB200Error):
+            call()
+    assert {n for n in B.ops.__all__ if not n.startswith(("EPI_", "ROPE_"))} >= {
+        "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32", "patchify", "unpatchify",
+        "sinusoidal_embedding", "gemv_f32", "cfg_euler_step", "head_norms"}
