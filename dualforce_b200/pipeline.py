@@ -391,4 +391,23 @@ def swap_modules(pipe) -> int:
             model.head = step.Head.from_reference(model.head)
             count += 1
     step.bind(pipe)
+    # scripts/inference_single.py:102-117 calls pipe.replace_attention() when cp_size > 1; on an installed pipeline that
+    # must not put the reference's yunchang-backed USPAttention back into the modules (context parallelism is handled
+    # from cp_mesh here), so the method keeps its contract -- it returns the number of attention sites -- and leaves
+    # the B200 processors where they are.
+    pipe.replace_attention = types.MethodType(_replace_attention_noop, pipe)
     return count
+
+
+def _replace_attention_noop(self, attn_type=None) -> int:
+    """``MOVA.replace_attention`` (pipeline_mova.py:124-148) on an installed pipeline: counts the same sites the
+    reference would replace and replaces nothing."""
+    n = 0
+    for name in ("video_dit", "video_dit_2", "audio_dit"):
+        model = getattr(self, name, None)
+        if model is not None:
+            n += len(model.blocks)
+    bridge = getattr(self, "dual_tower_bridge", None)
+    if bridge is not None:
+        n += len(bridge.audio_to_video_conditioners) + len(bridge.video_to_audio_conditioners)
+    return n

@@ -210,6 +210,11 @@ def test_swap_modules_on_reference_pipeline_runs_the_reference_loop_shape(emu, s
     assert n == cfg["visual_layers"] + cfg["audio_layers"] + n_bridge + 2
     assert isinstance(vis.head, step.Head) and isinstance(pipe.dual_tower_bridge, pl.DualTowerConditionalBridge)
     assert pl.swap_modules(pipe) == 0  # idempotent
+    # the script's own `pipe.replace_attention(...)` call (inference_single.py:115) keeps its return contract and
+    # leaves the B200 attention processors in place
+    sites = cfg["visual_layers"] + cfg["audio_layers"] + n_bridge
+    assert pipe.replace_attention(attn_type="fa") == sites
+    assert type(vis.blocks[0].self_attn.attn).__module__.startswith("dualforce_b200")
     v, a = pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"],
                                       audio_latents=inp["audio_latents"], context=inp["context"].to(torch.bfloat16),
                                       timestep=inp["timestep"], audio_timestep=None, video_fps=cfg["video_fps"])
