@@ -178,3 +178,27 @@ def test_sp_helper_twins_match_reference_golden(meta):
     assert (cl, pl, tot) == (6, 3, 21) and torch.equal(c0[:3], tab[18:]) and torch.equal(c0[3:], torch.zeros(3, 1, 4))
     sel = cp._sp_select_rank(x, sp_size=4, sp_rank=3, chunk_len=6, pad_len=3)
     assert torch.equal(sel, chunks[3])
+
+
+def test_activation_hook_installs_on_first_call(monkeypatch):
+    """dualforce_b200.launch.activate: the wrapped __call__ installs once, then defers to the original."""
+    import dualforce_b200
+    from dualforce_b200 import launch
+
+    calls = []
+
+    class FakeMOVA:
+        def __call__(self, prompt, steps=1):
+            calls.append(("call", prompt, steps))
+            return "video"
+
+    monkeypatch.setattr(dualforce_b200, "install", lambda pipe, cuda_graph=False: calls.append(("install", cuda_graph)) or 0)
+    cls = launch.activate(FakeMOVA)
+    assert launch.activate(FakeMOVA) is cls  # idempotent
+    pipe = FakeMOVA()
+    assert pipe("a", steps=2) == "video" and pipe("b") == "video"
+    assert calls == [("install", False), ("call", "a", 2), ("call", "b", 1)]
+    other = FakeMOVA()
+    monkeypatch.setenv("MOVA_B200_CUDA_GRAPH", "1")
+    other("c")
+    assert calls[-2:] == [("install", True), ("call", "c", 1)]
