@@ -193,7 +193,11 @@ class CrossAttention(nn.Module):
         w, b = self._kv.get([self.k, self.v])
         static = getattr(y, "_mova_b200_static", False)
         if static:
-            key = (y.data_ptr(), tuple(y.shape), y._version, w.data_ptr())
+            try:
+                version = y._version
+            except RuntimeError:  # inference-mode tensor
+                version = -1
+            key = (y.data_ptr(), tuple(y.shape), version, w.data_ptr())
             memo = self.__dict__.setdefault("_kv_memo", {})
             hit = memo.get(key)
             if hit is not None:

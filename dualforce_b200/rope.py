@@ -31,7 +31,11 @@ def set_cache(enabled: bool) -> None:
 
 
 def _key(t: torch.Tensor) -> tuple:
-    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version, str(t.device))
+    try:
+        version = t._version
+    except RuntimeError:  # inference-mode tensors carry no version counter (and cannot be modified in place)
+        version = -1
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, version, str(t.device))
 
 
 def _remember(key: tuple, sources: tuple, value):

@@ -44,8 +44,15 @@ __all__ = ["Head", "WanModel", "WanAudioModel", "inference_single_step", "embed_
 _STATIC_FLAG = "_mova_b200_static"  # set on context embeddings whose per-layer k / v may be memoised
 
 
+def _version(t: torch.Tensor) -> int:
+    try:
+        return t._version
+    except RuntimeError:  # inference-mode tensors carry no version counter (and cannot be modified in place)
+        return -1
+
+
 def _tensor_key(t: torch.Tensor) -> tuple:
-    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version, str(t.device))
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, _version(t), str(t.device))
 
 
 class _Memo:
