@@ -17,7 +17,11 @@ for v in v3 v7 v8; do
     MOVA_ATTN_VARIANT=$v MOVA_ATTN_BOUNDED=$b timeout 60 ./selftest attn 1 43120 43120 40 3
   done
 done > ../../gpurun_out/r2_attn_variants.log 2>&1
-# polynomial-exp2 share on the best schedule (the variants are compiled at EMU = 4 only; v3 takes MOVA_ATTN_EMU)
+# polynomial-exp2 share on the best schedule (variants: MOVA_ATTN_EMU = 0 / 4 / 8; v3 also 2 / 6)
+for e in 0 8; do
+  echo "== v8 bounded EMU $e"
+  MOVA_ATTN_VARIANT=v8 MOVA_ATTN_BOUNDED=1 MOVA_ATTN_EMU=$e timeout 60 ./selftest attn 1 43120 43120 40 3
+done >> ../../gpurun_out/r2_attn_variants.log 2>&1
 cd ../..
 
 # 3. the bench with the winner (example: v8 + bounded), then the default for an A/B on the same box

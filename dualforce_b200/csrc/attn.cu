@@ -565,14 +565,23 @@ extern "C" int mova_b200_attn_fwd_ex(const void* q, int64_t q_bs, int64_t q_ss, 
     }
     return 0;
   }
+  // the experimental schedules come with the polynomial-exp2 share 0 / 25 % / 50 % (MOVA_ATTN_EMU = 0 / 4 / 8): once
+  // the row maximum and part of the MMA chain are off the softmax path, the MUFU unit is the next thing to balance
+#define MV_ATTN_EXP(QS, BND)                                                                        \
+  do {                                                                                              \
+    if (emu == 0) return launch_attn<0, false, QS, BND>(grid, st, tmQ, tmK, tmV, tmO, p);           \
+    if (emu == 8) return launch_attn<8, false, QS, BND>(grid, st, tmQ, tmK, tmV, tmO, p);           \
+    return launch_attn<AT_DEFAULT_EMU, false, QS, BND>(grid, st, tmQ, tmK, tmV, tmO, p);            \
+  } while (0)
   if (q_norm != nullptr && variant != 6) {  // bounded softmax (experimental): any of the schedules of this file
-    if (variant == 7) return launch_attn<AT_DEFAULT_EMU, false, 1, true>(grid, st, tmQ, tmK, tmV, tmO, p);
-    if (variant == 8) return launch_attn<AT_DEFAULT_EMU, false, 2, true>(grid, st, tmQ, tmK, tmV, tmO, p);
-    return launch_attn<AT_DEFAULT_EMU, false, 0, true>(grid, st, tmQ, tmK, tmV, tmO, p);
+    if (variant == 7) MV_ATTN_EXP(1, true);
+    if (variant == 8) MV_ATTN_EXP(2, true);
+    MV_ATTN_EXP(0, true);
   }
   if (variant == 6) return launch_attn_v6(grid, st, tmQ, tmK, tmV, tmO, p, emu);
-  if (variant == 7) return launch_attn<AT_DEFAULT_EMU, false, 1>(grid, st, tmQ, tmK, tmV, tmO, p);
-  if (variant == 8) return launch_attn<AT_DEFAULT_EMU, false, 2>(grid, st, tmQ, tmK, tmV, tmO, p);
+  if (variant == 7) MV_ATTN_EXP(1, false);
+  if (variant == 8) MV_ATTN_EXP(2, false);
+#undef MV_ATTN_EXP
   switch (emu) {
     case 0: return launch_attn<0, false>(grid, st, tmQ, tmK, tmV, tmO, p);
     case 2: return launch_attn<2, false>(grid, st, tmQ, tmK, tmV, tmO, p);
