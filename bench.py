@@ -227,7 +227,7 @@ def build_model(cfg, device, seed=0, with_step=False):
     return pipe
 
 
-def host_step_inputs(cfg, seed=2):
+def host_step_inputs(cfg, seed=2, pin=True):
     """Pinned host tensors of one denoising step as MOVA.__call__ hands them to inference_single_step
     (pipeline_mova.py:416-437): fp32 latents (16 noise + 20 condition channels), fp32 audio latents, the two T5
     prompt embeddings [1, 512, 4096] bf16, the timestep."""
@@ -236,14 +236,14 @@ def host_step_inputs(cfg, seed=2):
     g = torch.Generator().manual_seed(seed)
     f, h, w = cfg["grid_size"]
     pt, ph, pw = STEP_360P["visual_patch"]
-    inp = {"visual_latents": torch.randn(1, STEP_360P["visual_in_dim"], f * pt, h * ph, w * pw, generator=g).pin_memory(),
-           "audio_latents": torch.randn(1, STEP_360P["audio_in_dim"], cfg["audio_len"], generator=g).pin_memory(),
-           "timestep": torch.tensor([900.0], dtype=torch.float32).pin_memory()}
+    inp = {"visual_latents": torch.randn(1, STEP_360P["visual_in_dim"], f * pt, h * ph, w * pw, generator=g),
+           "audio_latents": torch.randn(1, STEP_360P["audio_in_dim"], cfg["audio_len"], generator=g),
+           "timestep": torch.tensor([900.0], dtype=torch.float32)}
     for name in ("pos", "neg"):
         c = torch.randn(1, cfg["text_len"], STEP_360P["text_dim"], generator=g)
         c[:, 64:] = 0  # zero-padded T5 tokens (pipeline_mova.py:309-312)
-        inp[f"context_{name}"] = c.to(torch.bfloat16).pin_memory()
-    return inp
+        inp[f"context_{name}"] = c.to(torch.bfloat16)
+    return {k: v.pin_memory() for k, v in inp.items()} if pin else inp
 
 
 def host_inputs(cfg, seed=1):
@@ -275,6 +275,59 @@ def host_inputs(cfg, seed=1):
 
 def nbytes(t):
     return t.numel() * t.element_size()
+
+
+def measure_step_api(pipe, cfg, device, cp_mesh, rank, steps, timed, launches, pin=True):
+    """The e2e leg through the step-level public API, the call MOVA.__call__ makes per scheduler iteration
+    (pipeline_mova.py:429-456): 2 x ``pipe.inference_single_step`` with fp32 latents + a fresh timestep copied from
+    pinned host memory inside the timed region and the bf16 denoised latents copied back (reporting rank only; the
+    result is replicated across cp ranks).  ``timed(fn, steps)`` is the bench's barrier / CUDA-event timer,
+    ``launches()`` the running count of kernel launches.  Returns the ``e2e`` object of the JSON line."""
+    import torch
+
+    def pinned(t):
+        return t.pin_memory() if pin else t
+
+    host_s = {k: pinned(v) for k, v in host_step_inputs(cfg, pin=False).items()}
+    out_host = []
+    # a new timestep every step, like the scheduler loop (one pinned scalar each: an async copy never reads a buffer
+    # the host has since rewritten)
+    ts_host = [pinned(torch.tensor([900.0 - 18.0 * i], dtype=torch.float32)) for i in range(steps + 4)]
+    ts_next = [0]
+    # the two prompt embeddings are uploaded once per video, as in MOVA.__call__ (:404-405), not once per step
+    ctx_dev = {w_: host_s[f"context_{w_}"].to(device) for w_ in ("pos", "neg")}
+
+    def step_e2e_api():
+        ts = ts_host[ts_next[0] % len(ts_host)]
+        ts_next[0] += 1
+        d = {k: host_s[k].to(device, non_blocking=True) for k in ("visual_latents", "audio_latents")}
+        d["timestep"] = ts.to(device, non_blocking=True)
+        outs = []
+        for which in ("pos", "neg"):
+            outs.append(pipe.inference_single_step(
+                visual_dit=pipe.video_dit, visual_latents=d["visual_latents"], audio_latents=d["audio_latents"],
+                context=ctx_dev[which], timestep=d["timestep"], audio_timestep=None, video_fps=cfg["video_fps"],
+                cp_mesh=cp_mesh))
+        if not out_host:
+            out_host.extend([pinned(torch.empty(t.shape, dtype=t.dtype)) for t in pair] for pair in outs)
+        if rank == 0:
+            for pair, hpair in zip(outs, out_host):
+                for t, ht in zip(pair, hpair):
+                    ht.copy_(t, non_blocking=True)
+        return outs
+
+    step_e2e_api()  # first step: fills the prompt memos (text embedding, per-layer text k / v)
+    step_e2e_api()
+    before = launches()
+    step_e2e_api()
+    launches_per_step = launches() - before  # one steady-state step
+    ms_api = timed(step_e2e_api, steps)
+    per_step_in = sum(nbytes(host_s[k]) for k in ("visual_latents", "audio_latents")) + nbytes(ts_host[0])
+    return {"value": 1e3 / (ms_api / steps), "unit": UNIT, "h2d_bytes_per_step": per_step_in,
+            "d2h_bytes_per_step": sum(nbytes(t) for pair in out_host for t in pair), "ms_per_step": ms_api / steps,
+            "gpu_launches_per_step": launches_per_step,
+            "api": "2 x pipe.inference_single_step (pipeline_mova.py:500-609 drop-in): fp32 latents + timestep from "
+                   "pinned host memory in, bf16 denoised latents out; prompt embeddings resident (uploaded once per video)"}
 
 
 def run_b200_arm(args):
@@ -448,48 +501,7 @@ def run_b200_arm(args):
     e2e_step = None
     if want_step_api and step_api_error is None:
         try:
-            host_s = host_step_inputs(cfg)
-            out_host_s = None
-            # a new timestep every step, like the scheduler loop (one pinned scalar each: an async copy never reads a
-            # buffer the host has since rewritten)
-            ts_host = [torch.tensor([900.0 - 18.0 * i], dtype=torch.float32).pin_memory() for i in range(args.steps + 4)]
-            ts_next = [0]
-
-            def step_e2e_api():
-                nonlocal out_host_s
-                host_s["timestep"] = ts_host[ts_next[0] % len(ts_host)]
-                ts_next[0] += 1
-                d = {k: v.to(device, non_blocking=True) for k, v in host_s.items() if not k.startswith("context_")}
-                outs = []
-                for which in ("pos", "neg"):
-                    outs.append(pipe.inference_single_step(
-                        visual_dit=pipe.video_dit, visual_latents=d["visual_latents"], audio_latents=d["audio_latents"],
-                        context=ctx_dev[which], timestep=d["timestep"], audio_timestep=None, video_fps=cfg["video_fps"],
-                        cp_mesh=cp_mesh))
-                if out_host_s is None:
-                    out_host_s = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in pair] for pair in outs]
-                if rank == 0:
-                    for pair, hpair in zip(outs, out_host_s):
-                        for t, ht in zip(pair, hpair):
-                            ht.copy_(t, non_blocking=True)
-                return outs
-
-            # the two prompt embeddings are uploaded once per video, as in MOVA.__call__ (:404-405), not once per step
-            ctx_dev = {w_: host_s[f"context_{w_}"].to(device) for w_ in ("pos", "neg")}
-            launches1 = _lib.LAUNCHES
-            step_e2e_api()  # first step: fills the prompt memos (text embedding, per-layer text k / v)
-            step_e2e_api()
-            launches_step_api = (_lib.LAUNCHES - launches1)
-            step_e2e_api()
-            launches_step_api = _lib.LAUNCHES - launches1 - launches_step_api  # launches of one steady-state step
-            ms_api = timed(step_e2e_api, args.steps)
-            per_step_in = sum(nbytes(host_s[k]) for k in ("visual_latents", "audio_latents", "timestep"))
-            e2e_step = {"value": 1e3 / (ms_api / args.steps), "unit": UNIT, "h2d_bytes_per_step": per_step_in,
-                        "d2h_bytes_per_step": sum(nbytes(t) for pair in out_host_s for t in pair),
-                        "ms_per_step": ms_api / args.steps, "gpu_launches_per_step": launches_step_api,
-                        "api": "2 x pipe.inference_single_step (pipeline_mova.py:500-609 drop-in): fp32 latents + "
-                               "timestep from pinned host memory in, bf16 denoised latents out; prompt embeddings "
-                               "resident (uploaded once per video)"}
+            e2e_step = measure_step_api(pipe, cfg, device, cp_mesh, rank, args.steps, timed, lambda: _lib.LAUNCHES)
         except Exception as exc:
             step_api_error = repr(exc)[:300]
 

@@ -240,6 +240,23 @@ def test_bench_model_builder_composes_with_the_step(emu):
                                       timestep=torch.tensor([900.0]), audio_timestep=None, video_fps=24.0)
     assert v.shape == (1, S["visual_out_dim"], 2, 4, 6) and a.shape == (1, S["audio_out_dim"], 9)
     assert torch.isfinite(v.float()).all() and torch.isfinite(a.float()).all()
+    # the bench's step-level e2e leg itself (host logic: buffers, memo warm-up, launch accounting, JSON object)
+    import time
+
+    def timed(fn, steps):
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        return (time.perf_counter() - t0) * 1e3
+
+    e2e = bench.measure_step_api(pipe, cfg, torch.device("cpu"), None, 0, 2, timed, lambda: sum(emu.values()), pin=False)
+    assert e2e["value"] > 0 and e2e["unit"] == "steps/s" and e2e["ms_per_step"] > 0
+    assert e2e["h2d_bytes_per_step"] == (36 * 2 * 4 * 6 + S["audio_in_dim"] * 9 + 1) * 4
+    assert e2e["d2h_bytes_per_step"] == 2 * (16 * 2 * 4 * 6 + S["audio_out_dim"] * 9) * 2
+    n_blocks = cfg["visual_layers"] + cfg["audio_layers"]
+    per_forward = 17 * n_blocks + 14 * min(cfg["visual_layers"], cfg["audio_layers"]) - 2 * n_blocks  # text k/v memoised
+    # + per forward: 2 patchify + 2 patch GEMMs + 2 x (add, LN, GEMM, unpatchify) heads; per step: 2 x 4 time kernels
+    assert e2e["gpu_launches_per_step"] == 2 * (per_forward + 4 + 8) + 8, e2e
     # the forward-level builder is unchanged
     bare = bench.build_model(cfg, torch.device("cpu"), with_step=False)
     assert not hasattr(bare.video_dit, "patch_embedding") and not hasattr(bare, "inference_single_step")
