@@ -137,6 +137,33 @@ def run_reference_step(cfg, seed):
     return {k: t.detach().numpy() for k, t in out.items()}, O.checksum(Pv, Pa, Pb, inp), keys
 
 
+def sample_indices(numel: int, n: int, seed: int = 0):
+    """Fixed pseudo-random flat indices into a tensor of ``numel`` elements (shared by the generator and the tests)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, numel, (n,), generator=g)
+
+
+@torch.no_grad()
+def run_reference_reduced(cfg, seed):
+    """BASELINE.json configs[0]: the reference's dual-tower forward at MOVA-360p WIDTHS and reduced depth (2 + 2 blocks,
+    2 bridge layers, 352x640x17-frame clip: L_v = 4400, L_a = 36, 512 text tokens), fp32 on CPU.  The outputs are 90 MB,
+    so the fixture keeps 8192 + 2048 sampled elements and whole-tensor statistics."""
+    Pv, Pa, Pb, inp = O.make_case(cfg, seed)
+    R, vis, aud, bridge, pipe = build_reference(cfg, Pv, Pa, Pb)
+    fv, fa = R.forward_dual_tower_dit(
+        pipe, visual_dit=vis, visual_x=inp["visual_x"], audio_x=inp["audio_x"], visual_context=inp["visual_context"],
+        audio_context=inp["audio_context"], visual_t_mod=inp["visual_t_mod"], audio_t_mod=inp["audio_t_mod"],
+        visual_freqs=inp["visual_freqs"], audio_freqs=inp["audio_freqs"], grid_size=cfg["grid_size"],
+        video_fps=cfg["video_fps"])
+    out = {}
+    for name, t, n in (("visual", fv, 8192), ("audio", fa, 2048)):
+        idx = sample_indices(t.numel(), n, seed=11)
+        out[f"{name}_samples"] = t.reshape(-1)[idx]
+        out[f"{name}_stats"] = torch.tensor([t.mean().item(), t.std().item(), t.abs().max().item(), t.norm().item()])
+        out[f"{name}_delta_samples"] = (t - inp[f"{name if name == 'audio' else 'visual'}_x"]).reshape(-1)[idx]
+    return {k: v.numpy() for k, v in out.items()}, O.checksum(Pv, Pa, Pb, inp)
+
+
 def main():
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -148,6 +175,15 @@ def main():
         with open(os.path.join(out_dir, name + ".json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)
         print(name, {k: v.shape for k, v in arrays.items()}, "checksum", csum)
+    if os.environ.get("MOVA_GOLDEN_REDUCED", "1") == "1":  # ~1 minute and ~6 GB of RAM on 8 cores
+        arrays, csum = run_reference_reduced(O.REDUCED_360P_CFG, 2024)
+        meta = dict(cfg=O.REDUCED_360P_CFG, seed=2024, checksum=csum, torch=torch.__version__, sample_seed=11,
+                    source="reference DiTBlocks / bridge + MOVA.forward_dual_tower_dit at MOVA-360p widths (BASELINE "
+                           "configs[0]) run in fp32 on CPU by oracle/make_golden.py; sampled elements + statistics")
+        np.savez_compressed(os.path.join(out_dir, "reduced_360p_samples.npz"), **arrays)
+        with open(os.path.join(out_dir, "reduced_360p_samples.json"), "w") as f:
+            json.dump(meta, f, indent=1, sort_keys=True)
+        print("reduced_360p_samples", {k: v.shape for k, v in arrays.items()}, "checksum", csum)
     for name, cfg, seed in (("tiny_step", O.TINY_STEP_CFG, 1234),):
         arrays, csum, keys = run_reference_step(cfg, seed)
         meta = dict(cfg=cfg, seed=seed, checksum=csum, torch=torch.__version__, reference_state_dict_keys=keys,
