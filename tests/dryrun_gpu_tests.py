@@ -57,6 +57,16 @@ def main():
         return orig_tensor_to(self, *args, **kwargs)
 
     torch.Tensor.to = tensor_to
+
+    def cpu_factory(fn):
+        def wrapped(*args, **kwargs):
+            if "device" in kwargs:
+                kwargs["device"] = _cpu_device(kwargs["device"])
+            return fn(*args, **kwargs)
+        return wrapped
+
+    for name in ("tensor", "ones", "zeros", "empty", "randn", "arange", "full"):
+        setattr(torch, name, cpu_factory(getattr(torch, name)))
     args = sys.argv[1:] or [os.path.join(HERE, "test_gpu_step.py"), "-k", "not context_parallel"]
     return pytest.main(["-q", "--runxfail", "-m", "gpu", "-p", "no:cacheprovider", *args])
 
