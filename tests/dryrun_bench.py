@@ -84,6 +84,14 @@ def main():
         return out
 
     dualforce_b200.ops.attention = attention
+    # multi-rank dry run (torchrun --nproc-per-node 2 tests/dryrun_bench.py --gpus 2 ...): gloo instead of NCCL
+    import torch.distributed as dist
+    import torch.distributed.device_mesh as device_mesh
+
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend=None, **kw: real_init("gloo", **{k: v for k, v in kw.items() if k != "device_id"})
+    real_mesh = device_mesh.init_device_mesh
+    device_mesh.init_device_mesh = lambda device_type, *a, **kw: real_mesh("cpu", *a, **kw)
     del bench_torch
     sys.argv = [sys.argv[0]] + (sys.argv[1:] or ["--video-layers", "1", "--audio-layers", "1", "--frames", "5",
                                                  "--steps", "1", "--warmup", "3"])
