@@ -76,3 +76,34 @@ def test_every_ops_entry_point_rejects_cpu_tensors():
     assert {n for n in B.ops.__all__ if not n.startswith(("EPI_", "ROPE_"))} >= {
         "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32", "patchify", "unpatchify",
         "sinusoidal_embedding", "gemv_f32", "cfg_euler_step", "head_norms"}
+
+
+def test_ctypes_signatures_match_the_header_argument_by_argument():
+    """Every prototype of include/mova_b200.h against dualforce_b200._lib.SIGNATURES: same arity, and pointer /
+    int / int64_t / float arguments bound as c_void_p / c_int / c_int64 / c_float in the same positions (a swapped
+    int64 stride or float would otherwise only show as garbage on the device)."""
+    import ctypes
+
+    from dualforce_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "mova_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    seen = 0
+    for m in re.finditer(r"\b(mova_b200_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        params = [] if args in ("void", "") else [a.strip() for a in args.split(",")]
+        want = []
+        for prm in params:
+            if "*" in prm:
+                want.append(ctypes.c_void_p)
+            elif prm.startswith("int64_t"):
+                want.append(ctypes.c_int64)
+            elif prm.startswith("int"):
+                want.append(ctypes.c_int)
+            elif prm.startswith("float"):
+                want.append(ctypes.c_float)
+            else:
+                raise AssertionError(f"{name}: unrecognised parameter type in '{prm}'")
+        assert _lib.SIGNATURES[name][1] == want, f"{name}: header {params} vs ctypes {_lib.SIGNATURES[name][1]}"
+        seen += 1
+    assert seen == len(_lib.SIGNATURES)
