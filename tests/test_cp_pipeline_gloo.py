@@ -47,6 +47,8 @@ def _worker(rank, world, port, grid, results):
         for name, fn in emulated_ops.ENTRY_POINTS.items():
             setattr(real_ops, name, fn)
         cfg = dict(O.TINY_STEP_CFG, grid_size=grid)
+        if cfg["visual_heads"] % world:  # one video head per rank
+            cfg.update(visual_heads=world, visual_dim=128 * world, visual_ffn=192 * world)
         Pv, Pa, Pb, inp = O.make_step_case(cfg, 77)
         Pv, Pa, Pb = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb)
         ctx = inp["context"].to(torch.bfloat16)
@@ -73,10 +75,10 @@ def _worker(rank, world, port, grid, results):
         # the reference-style pad / gather helpers (functional.py:55-112 twins) across the two ranks
         from dualforce_b200 import cp
 
-        tab = torch.arange(1 * 7 * 4, dtype=torch.float32).reshape(1, 7, 4)  # 7 rows over 2 ranks: 4 + (3 + 1 pad)
+        tab = torch.arange(1 * 7 * 4, dtype=torch.float32).reshape(1, 7, 4)  # 7 rows: 4 + (3 + 1 pad) / 2 + 2 + 2 + (1 + 1)
         chunk, chunk_len, pad_len, total = cp._sp_split_tensor(tab, sp_size=world, sp_rank=rank)
         sp_ok = bool(torch.equal(cp._sp_all_gather_avg(chunk, sp_group=None, pad_len=pad_len), tab)
-                     and (chunk_len, pad_len, total) == (4, 1, 7))
+                     and (chunk_len, pad_len, total) == ((4, 1, 7) if world == 2 else (2, 1, 7)))
         results[rank] = dict(sp_ok=sp_ok, 
             cp_vs_oracle_v=metrics(v2, rv), cp_vs_oracle_a=metrics(a2, ra), cp_vs_cp1_v=metrics(v2, v1.float()),
             cp_vs_cp1_a=metrics(a2, a1.float()), shapes=(tuple(v2.shape), tuple(a2.shape), tuple(full_v.shape)),
@@ -85,16 +87,18 @@ def _worker(rank, world, port, grid, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("grid", [(3, 4, 5), (1, 3, 3)])  # 60 tokens -> 30 + 30; 9 tokens -> 5 + 4 (ragged)
-def test_step_context_parallel_world2(grid):
+# 60 tokens -> 30 + 30; 9 tokens -> 5 + 4 (ragged); 4 ranks: 18 tokens -> 5 + 5 + 5 + 3, one video head per rank
+@pytest.mark.parametrize("world,grid", [(2, (3, 4, 5)), (2, (1, 3, 3)), (4, (2, 3, 3))])
+def test_step_context_parallel_gloo(world, grid):
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), grid, results), nprocs=2, join=True)
-    assert len(results) == 2
+    mp.spawn(_worker, args=(world, _free_port(), grid, results), nprocs=world, join=True)
+    assert len(results) == world
     f, h, w = grid
-    for rank in (0, 1):
+    dim = 256 if world == 2 else 128 * world
+    for rank in range(world):
         r = results[rank]
-        assert r["shapes"] == ((1, 16, f, 2 * h, 2 * w), (1, 32, 21), (1, f * h * w, 256))
+        assert r["shapes"] == ((1, 16, f, 2 * h, 2 * w), (1, 32, 21), (1, f * h * w, dim))
         for key in ("cp_vs_oracle_v", "cp_vs_oracle_a"):
             m = r[key]
             assert m["finite"] and m["ratio"] <= 3e-2 and m["rel_fro"] <= 1.5e-2, (rank, key, m)
@@ -105,4 +109,5 @@ def test_step_context_parallel_world2(grid):
         assert r["calls"]["lse_merge"] == 2
         assert r["sp_ok"]
     # every rank ends with the same full-length outputs
-    assert torch.equal(results[0]["v2"], results[1]["v2"]) and torch.equal(results[0]["a2"], results[1]["a2"])
+    for rank in range(1, world):
+        assert torch.equal(results[0]["v2"], results[rank]["v2"]) and torch.equal(results[0]["a2"], results[rank]["a2"])
