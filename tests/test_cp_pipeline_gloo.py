@@ -35,7 +35,7 @@ class _Mesh:
         return self._world
 
 
-def _worker(rank, world, port, grid, results):
+def _worker(rank, world, port, grid, heads, results):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -47,8 +47,8 @@ def _worker(rank, world, port, grid, results):
         for name, fn in emulated_ops.ENTRY_POINTS.items():
             setattr(real_ops, name, fn)
         cfg = dict(O.TINY_STEP_CFG, grid_size=grid)
-        if cfg["visual_heads"] % world:  # one video head per rank
-            cfg.update(visual_heads=world, visual_dim=128 * world, visual_ffn=192 * world)
+        if heads is not None:  # e.g. 4 heads on 2 ranks: two head groups per rank, exchanged one after the other
+            cfg.update(visual_heads=heads, visual_dim=128 * heads, visual_ffn=192 * heads)
         Pv, Pa, Pb, inp = O.make_step_case(cfg, 77)
         Pv, Pa, Pb = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb)
         ctx = inp["context"].to(torch.bfloat16)
@@ -88,14 +88,15 @@ def _worker(rank, world, port, grid, results):
 
 
 # 60 tokens -> 30 + 30; 9 tokens -> 5 + 4 (ragged); 4 ranks: 18 tokens -> 5 + 5 + 5 + 3, one video head per rank
-@pytest.mark.parametrize("world,grid", [(2, (3, 4, 5)), (2, (1, 3, 3)), (4, (2, 3, 3))])
-def test_step_context_parallel_gloo(world, grid):
+@pytest.mark.parametrize("world,grid,heads", [(2, (3, 4, 5), None), (2, (1, 3, 3), None), (2, (2, 3, 3), 4),
+                                              (4, (2, 3, 3), 4)])
+def test_step_context_parallel_gloo(world, grid, heads):
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), grid, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), grid, heads, results), nprocs=world, join=True)
     assert len(results) == world
     f, h, w = grid
-    dim = 256 if world == 2 else 128 * world
+    dim = 256 if heads is None else 128 * heads
     for rank in range(world):
         r = results[rank]
         assert r["shapes"] == ((1, 16, f, 2 * h, 2 * w), (1, 32, 21), (1, f * h * w, dim))
