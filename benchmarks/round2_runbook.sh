@@ -37,3 +37,14 @@ MOVA_V2A_SPLITS=5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpuru
 
 # 5. BASELINE configs[4]
 python benchmarks/bridge_microbench.py --quick > gpurun_out/r2_bridge_microbench.jsonl 2>&1
+
+# 6. ncu evidence still missing from profiles/: the GEMM and the memory-bound kernels (tensor-pipe % / DRAM GB/s),
+#    one capture each after the plain command has exited 0 (B200_PROFILING.md recipe)
+cd dualforce_b200/csrc
+./selftest gemm 1 0 43120 15360 5120 3 && ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 1 \
+  -o ../../gpurun_out/r2_gemm_qkv ./selftest gemm 1 0 43120 15360 5120 3 > ../../gpurun_out/r2_ncu_gemm.log 2>&1
+./selftest ln 43120 5120 0 1 && ncu --set full --clock-control none --import-source on -k regex:layernorm -c 1 \
+  -o ../../gpurun_out/r2_layernorm ./selftest ln 43120 5120 0 1 > ../../gpurun_out/r2_ncu_ln.log 2>&1
+./selftest rr 43120 5120 1 && ncu --set full --clock-control none --import-source on -k regex:rmsnorm_rope -c 1 \
+  -o ../../gpurun_out/r2_rmsnorm_rope ./selftest rr 43120 5120 1 > ../../gpurun_out/r2_ncu_rr.log 2>&1
+cd ../..
