@@ -5,11 +5,20 @@
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU cores
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # context parallel (cp_size = N) over NCCL
 
-A "step" is what ``MOVA.__call__`` does per scheduler iteration at cfg_scale > 1 (pipeline_mova.py:429-456): two
-forwards of the dual-tower DiT (positive and negative prompt, B = 1 each) through ``forward_dual_tower_dit``
-(pipeline_mova.py:612-711) on the full MOVA-360p geometry: 40 video blocks (5120 / 40 heads / ffn 13824), 30 audio
-blocks (1536 / 12 / 8960), 30 bridge layers in both directions, L_v = 49x22x40 = 43120 video tokens, L_a = 403 audio
-tokens, 512 text tokens, bf16, random-init weights, synthetic latents (there is no checkpoint in this sandbox).
+A "step" is what ``MOVA.__call__`` does per scheduler iteration at cfg_scale > 1 (pipeline_mova.py:416-475): two
+``inference_single_step`` calls (positive and negative prompt, B = 1 each: time / text embeddings, patchify, the
+dual-tower forward ``forward_dual_tower_dit`` of pipeline_mova.py:612-711, head, unpatchify), classifier-free
+guidance and the scheduler's Euler update of both latents -- on the full MOVA-360p geometry: 40 video blocks
+(5120 / 40 heads / ffn 13824), 30 audio blocks (1536 / 12 / 8960), 30 bridge layers in both directions,
+L_v = 49x22x40 = 43120 video tokens, L_a = 403 audio tokens, 512 text tokens, bf16, random-init weights, synthetic
+latents (there is no checkpoint in this sandbox).  Two video experts are resident (``video_dit`` / ``video_dit_2``,
+pipeline_mova.py:406-415), as in the reference's memory footprint.
+
+Before anything is timed, every rank runs BASELINE.json configs[0] (2 + 2 blocks at full widths, L_v = 4400) through
+the same code path -- context parallel when N > 1 -- and compares it with sampled outputs of the REFERENCE itself
+(``dualforce_b200.selfcheck``); the result is the ``parity`` object of the line and a failure exits non-zero.
+
+    python bench.py --gpus N --schedule 50        # BASELINE configs[2]: the whole 50-step denoising loop, timed as one
 
 One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every key.
 """
@@ -125,15 +134,17 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-CPU_SAMPLE_CFG = dict(FULL_360P, visual_layers=1, audio_layers=1, grid_size=(5, 22, 40), audio_len=36)
-CPU_SAMPLE_TEXT = ("1 video block + 1 audio block + 1 bridge layer (both directions) at full MOVA widths "
-                   "(5120/40, 1536/12), 352x640x17-frame clip (L_v=4400, L_a=36, 512 text tokens), fp32, "
-                   "torch CPU; steps/s = 1 / (sample seconds x FLOPs(full 360p step) / FLOPs(sample))")
+# BASELINE.md section 4 / BASELINE.json configs[0], run AS IS: 2 video + 2 audio blocks + 2 bridge layers at full widths
+CPU_CFG = dict(FULL_360P, visual_layers=2, audio_layers=2, grid_size=(5, 22, 40), audio_len=36)
+CPU_SAMPLE_TEXT = ("BASELINE configs[0] as is: 2 video + 2 audio blocks + 2 bridge layers (both directions) at full MOVA "
+                   "widths (5120/40, 1536/12), 352x640x17-frame clip (L_v=4400, L_a=36, 512 text tokens), fp32, torch "
+                   "CPU, all host cores; `measured` is that configuration's own rate, `value` its forward time scaled "
+                   "by FLOPs(full 360p CFG step) / FLOPs(configs[0] forward) -- an estimate, labelled as such")
 
 
 def cpu_sample_runner():
-    """Returns (run, scale): run() executes the bounded sample once and returns seconds; scale converts to the
-    full-step estimate."""
+    """Returns (run, scale, cores): run() executes ONE configs[0] forward and returns seconds; ``scale`` x seconds is
+    the estimated duration of the full MOVA-360p CFG step (2 forwards) by FLOP count."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
 
@@ -141,7 +152,7 @@ def cpu_sample_runner():
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = CPU_SAMPLE_CFG
+    cfg = CPU_CFG
     Pv, Pa, Pb, inp = O.make_case(cfg, 0)
 
     def run():
@@ -156,23 +167,39 @@ def cpu_sample_runner():
     return run, scale, cores
 
 
+def cpu_baseline_object(sec_forward, scale, cores):
+    return {"value": 1.0 / (sec_forward * scale), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": CPU_SAMPLE_TEXT,
+            "measured": {"config": "BASELINE configs[0] (2+2+2 layers, L_v=4400)", "seconds_per_forward": sec_forward,
+                         "steps_per_s": 1.0 / (FORWARDS_PER_STEP * sec_forward), "unit": "configs[0] CFG steps/s"},
+            "estimate": {"what": "full MOVA-360p CFG step", "flop_scale": scale,
+                         "seconds_per_step": sec_forward * scale}}
+
+
 def run_reference_arm(args):
+    """Each of the K timed 'steps' is one forward of configs[0] (the bounded sample); the line's value is the
+    FLOP-scaled estimate for the full step, the measured configs[0] rate is given beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     run, scale, cores = cpu_sample_runner()
     for _ in range(args.warmup):
         run()
+    t0 = time.perf_counter()
     times = [run() for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
     sec = sum(times) / len(times)
-    value = 1.0 / (sec * scale)
+    cb = cpu_baseline_object(sec, scale, cores)
+    value = cb["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * scale * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MOVA-360p full dual-tower denoising step (40 video / 30 audio / 30 bridge layers, "
-                               "L_v=43120, L_a=403), estimated from a bounded CPU sample", "sample_seconds": sec},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": CPU_SAMPLE_TEXT},
+                               "L_v=43120, L_a=403): ESTIMATED by FLOP count from the measured BASELINE configs[0] "
+                               "forward (2+2+2 layers, L_v=4400); each timed step of this arm = one configs[0] forward",
+                   "measured_seconds_per_configs0_forward": sec, "timed_region_s": wall},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -182,7 +209,12 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------------
-def build_model(cfg, device, seed=0, with_step=False):
+def build_model(cfg, device, seed=0, experts=1):
+    """WanModel / WanAudioModel / bridge twins with random-init bf16 weights on ``device`` and a pipeline-like
+    namespace with both drop-in methods bound.  ``experts=2`` also builds ``video_dit_2`` (the low-noise expert of
+    pipeline_mova.py:406-415) so that the memory footprint is the reference's."""
+    import types
+
     import torch
 
     import dualforce_b200 as B
@@ -190,55 +222,47 @@ def build_model(cfg, device, seed=0, with_step=False):
     torch.manual_seed(seed)
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
+
+    def video_tower():
+        return B.WanModel(dim=cfg["visual_dim"], in_dim=STEP_360P["visual_in_dim"], ffn_dim=cfg["visual_ffn"],
+                          out_dim=STEP_360P["visual_out_dim"], text_dim=STEP_360P["text_dim"],
+                          freq_dim=STEP_360P["freq_dim"], eps=cfg["eps"], patch_size=STEP_360P["visual_patch"],
+                          num_heads=cfg["visual_heads"], num_layers=cfg["visual_layers"], has_image_input=False)
+
     try:
         with torch.device(device):
-            vis = torch.nn.Module()
-            vis.blocks = torch.nn.ModuleList([B.DiTBlock(False, cfg["visual_dim"], cfg["visual_heads"], cfg["visual_ffn"],
-                                                         cfg["eps"]) for _ in range(cfg["visual_layers"])])
-            aud = torch.nn.Module()
-            aud.blocks = torch.nn.ModuleList([B.DiTBlock(False, cfg["audio_dim"], cfg["audio_heads"], cfg["audio_ffn"],
-                                                         cfg["eps"]) for _ in range(cfg["audio_layers"])])
-            if with_step:
-                # the rest of WanModel / WanAudioModel: embeddings, patch embedding, head -- what
-                # MOVA.inference_single_step drives around the path.  Zero-layer twins donate those parameters; the
-                # block lists above stay exactly as the forward-level measurement has always built them.
-                tv = B.WanModel(dim=cfg["visual_dim"], in_dim=STEP_360P["visual_in_dim"], ffn_dim=cfg["visual_ffn"],
-                                out_dim=STEP_360P["visual_out_dim"], text_dim=STEP_360P["text_dim"],
-                                freq_dim=STEP_360P["freq_dim"], eps=cfg["eps"], patch_size=STEP_360P["visual_patch"],
-                                num_heads=cfg["visual_heads"], num_layers=0, has_image_input=False)
-                ta = B.WanAudioModel(dim=cfg["audio_dim"], in_dim=STEP_360P["audio_in_dim"], ffn_dim=cfg["audio_ffn"],
-                                     out_dim=STEP_360P["audio_out_dim"], text_dim=STEP_360P["text_dim"],
-                                     freq_dim=STEP_360P["freq_dim"], eps=cfg["eps"], patch_size=STEP_360P["audio_patch"],
-                                     num_heads=cfg["audio_heads"], num_layers=0, has_image_input=False, vae_type="dac")
-                tv.blocks, ta.blocks = vis.blocks, aud.blocks
-                vis, aud = tv, ta
+            vis = video_tower()
+            vis2 = video_tower() if experts > 1 else None
+            aud = B.WanAudioModel(dim=cfg["audio_dim"], in_dim=STEP_360P["audio_in_dim"], ffn_dim=cfg["audio_ffn"],
+                                  out_dim=STEP_360P["audio_out_dim"], text_dim=STEP_360P["text_dim"],
+                                  freq_dim=STEP_360P["freq_dim"], eps=cfg["eps"], patch_size=STEP_360P["audio_patch"],
+                                  num_heads=cfg["audio_heads"], num_layers=cfg["audio_layers"], has_image_input=False,
+                                  vae_type="dac")
             bridge = B.DualTowerConditionalBridge(
                 visual_layers=cfg["visual_layers"], audio_layers=cfg["audio_layers"], visual_hidden_dim=cfg["visual_dim"],
                 audio_hidden_dim=cfg["audio_dim"], audio_fps=cfg["audio_fps"], head_dim=cfg["head_dim"],
                 interaction_strategy=cfg["interaction_strategy"], apply_cross_rope=cfg["apply_cross_rope"])
     finally:
         torch.set_default_dtype(prev)
-    import types
-
-    pipe = types.SimpleNamespace(video_dit=vis, video_dit_2=None, audio_dit=aud, dual_tower_bridge=bridge)
+    pipe = types.SimpleNamespace(video_dit=vis, video_dit_2=vis2, audio_dit=aud, dual_tower_bridge=bridge)
     pipe.forward_dual_tower_dit = types.MethodType(B.forward_dual_tower_dit, pipe)
-    if with_step:
-        pipe.inference_single_step = types.MethodType(B.inference_single_step, pipe)
+    pipe.inference_single_step = types.MethodType(B.inference_single_step, pipe)
     return pipe
 
 
 def host_step_inputs(cfg, seed=2, pin=True):
-    """Pinned host tensors of one denoising step as MOVA.__call__ hands them to inference_single_step
-    (pipeline_mova.py:416-437): fp32 latents (16 noise + 20 condition channels), fp32 audio latents, the two T5
-    prompt embeddings [1, 512, 4096] bf16, the timestep."""
+    """Host tensors of one denoising step as MOVA.__call__ holds them (pipeline_mova.py:378-437): fp32 noise latents
+    (16 ch), the mask + first-frame condition (20 ch), fp32 audio latents, the two T5 prompt embeddings
+    [1, 512, 4096] bf16."""
     import torch
 
     g = torch.Generator().manual_seed(seed)
     f, h, w = cfg["grid_size"]
     pt, ph, pw = STEP_360P["visual_patch"]
-    inp = {"visual_latents": torch.randn(1, STEP_360P["visual_in_dim"], f * pt, h * ph, w * pw, generator=g),
-           "audio_latents": torch.randn(1, STEP_360P["audio_in_dim"], cfg["audio_len"], generator=g),
-           "timestep": torch.tensor([900.0], dtype=torch.float32)}
+    n_lat = STEP_360P["visual_out_dim"]
+    inp = {"latents": torch.randn(1, n_lat, f * pt, h * ph, w * pw, generator=g),
+           "condition": torch.randn(1, STEP_360P["visual_in_dim"] - n_lat, f * pt, h * ph, w * pw, generator=g),
+           "audio_latents": torch.randn(1, STEP_360P["audio_in_dim"], cfg["audio_len"], generator=g)}
     for name in ("pos", "neg"):
         c = torch.randn(1, cfg["text_len"], STEP_360P["text_dim"], generator=g)
         c[:, 64:] = 0  # zero-padded T5 tokens (pipeline_mova.py:309-312)
@@ -246,88 +270,19 @@ def host_step_inputs(cfg, seed=2, pin=True):
     return {k: v.pin_memory() for k, v in inp.items()} if pin else inp
 
 
-def host_inputs(cfg, seed=1):
-    """Pinned host tensors of one step: shared latents/tables plus a positive and a negative text context."""
+def flow_match_schedule(num_steps, shift=5.0, num_train=1000, sigma_min=0.003 / 1.002, sigma_max=1.0):
+    """(timesteps, sigmas) of the reference's FlowMatchScheduler.set_timesteps in MOVA's configuration (shift 5,
+    extra_one_step; schedulers/flow_match.py:43-62): linspace then sigma' = s*sigma / (1 + (s-1)*sigma).  Only the
+    bench needs this (there is no reference scheduler on the GPU box); the product takes the scheduler's own lookups."""
     import torch
 
-    import dualforce_b200 as B
-
-    g = torch.Generator().manual_seed(seed)
-    f, h, w = cfg["grid_size"]
-    L_v, L_a, L_t = f * h * w, cfg["audio_len"], cfg["text_len"]
-    dv, da = cfg["visual_dim"], cfg["audio_dim"]
-
-    def rn(*shape, scale=1.0):
-        return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).pin_memory()
-
-    inp = {"visual_x": rn(1, L_v, dv), "audio_x": rn(1, L_a, da), "visual_t_mod": rn(1, 6, dv, scale=0.3),
-           "audio_t_mod": rn(1, 6, da, scale=0.3)}
-    for name in ("pos", "neg"):
-        cv, ca = torch.randn(1, L_t, dv, generator=g), torch.randn(1, L_t, da, generator=g)
-        cv[:, 64:] = 0  # zero-padded T5 tokens (pipeline_mova.py:309-312)
-        ca[:, 64:] = 0
-        inp[f"visual_context_{name}"] = cv.to(torch.bfloat16).pin_memory()
-        inp[f"audio_context_{name}"] = ca.to(torch.bfloat16).pin_memory()
-    inp["visual_freqs"] = B.rope.video_freqs(B.rope.precompute_freqs_cis_3d(cfg["head_dim"]), cfg["grid_size"], "cpu").contiguous().pin_memory()
-    inp["audio_freqs"] = B.rope.audio_freqs(B.rope.precompute_freqs_cis_1d(cfg["head_dim"]), L_a, "cpu").contiguous().pin_memory()
-    return inp
+    sig = torch.linspace(sigma_max, sigma_min, num_steps + 1)[:-1]
+    sig = shift * sig / (1 + (shift - 1) * sig)
+    return sig * num_train, sig
 
 
 def nbytes(t):
     return t.numel() * t.element_size()
-
-
-def measure_step_api(pipe, cfg, device, cp_mesh, rank, steps, timed, launches, pin=True):
-    """The e2e leg through the step-level public API, the call MOVA.__call__ makes per scheduler iteration
-    (pipeline_mova.py:429-456): 2 x ``pipe.inference_single_step`` with fp32 latents + a fresh timestep copied from
-    pinned host memory inside the timed region and the bf16 denoised latents copied back (reporting rank only; the
-    result is replicated across cp ranks).  ``timed(fn, steps)`` is the bench's barrier / CUDA-event timer,
-    ``launches()`` the running count of kernel launches.  Returns the ``e2e`` object of the JSON line."""
-    import torch
-
-    def pinned(t):
-        return t.pin_memory() if pin else t
-
-    host_s = {k: pinned(v) for k, v in host_step_inputs(cfg, pin=False).items()}
-    out_host = []
-    # a new timestep every step, like the scheduler loop (one pinned scalar each: an async copy never reads a buffer
-    # the host has since rewritten)
-    ts_host = [pinned(torch.tensor([900.0 - 18.0 * i], dtype=torch.float32)) for i in range(steps + 4)]
-    ts_next = [0]
-    # the two prompt embeddings are uploaded once per video, as in MOVA.__call__ (:404-405), not once per step
-    ctx_dev = {w_: host_s[f"context_{w_}"].to(device) for w_ in ("pos", "neg")}
-
-    def step_e2e_api():
-        ts = ts_host[ts_next[0] % len(ts_host)]
-        ts_next[0] += 1
-        d = {k: host_s[k].to(device, non_blocking=True) for k in ("visual_latents", "audio_latents")}
-        d["timestep"] = ts.to(device, non_blocking=True)
-        outs = []
-        for which in ("pos", "neg"):
-            outs.append(pipe.inference_single_step(
-                visual_dit=pipe.video_dit, visual_latents=d["visual_latents"], audio_latents=d["audio_latents"],
-                context=ctx_dev[which], timestep=d["timestep"], audio_timestep=None, video_fps=cfg["video_fps"],
-                cp_mesh=cp_mesh))
-        if not out_host:
-            out_host.extend([pinned(torch.empty(t.shape, dtype=t.dtype)) for t in pair] for pair in outs)
-        if rank == 0:
-            for pair, hpair in zip(outs, out_host):
-                for t, ht in zip(pair, hpair):
-                    ht.copy_(t, non_blocking=True)
-        return outs
-
-    step_e2e_api()  # first step: fills the prompt memos (text embedding, per-layer text k / v)
-    step_e2e_api()
-    before = launches()
-    step_e2e_api()
-    launches_per_step = launches() - before  # one steady-state step
-    ms_api = timed(step_e2e_api, steps)
-    per_step_in = sum(nbytes(host_s[k]) for k in ("visual_latents", "audio_latents")) + nbytes(ts_host[0])
-    return {"value": 1e3 / (ms_api / steps), "unit": UNIT, "h2d_bytes_per_step": per_step_in,
-            "d2h_bytes_per_step": sum(nbytes(t) for pair in out_host for t in pair), "ms_per_step": ms_api / steps,
-            "gpu_launches_per_step": launches_per_step,
-            "api": "2 x pipe.inference_single_step (pipeline_mova.py:500-609 drop-in): fp32 latents + timestep from "
-                   "pinned host memory in, bf16 denoised latents out; prompt embeddings resident (uploaded once per video)"}
 
 
 def run_b200_arm(args):
@@ -335,7 +290,8 @@ def run_b200_arm(args):
     import torch.distributed as dist
 
     import dualforce_b200 as B
-    from dualforce_b200 import _lib
+    from dualforce_b200 import _lib, selfcheck
+    from dualforce_b200 import step as bstep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -353,6 +309,35 @@ def run_b200_arm(args):
 
         cp_mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("cp",))
 
+    def finish(rc=0):
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            try:
+                dist.barrier()
+                torch.cuda.synchronize()
+                dist.destroy_process_group()
+            except Exception:  # noqa: BLE001 -- the line is out; a broken communicator must not change the exit code
+                pass
+        if rc:
+            sys.exit(rc)
+
+    # ---- parity gate: BASELINE configs[0] through this very code path (cp = world) vs the reference's samples ----
+    parity = None
+    if not args.no_parity:
+        parity = selfcheck.reduced_360p_parity(device, cp_mesh)
+        if world > 1:  # every rank must agree before anything is timed
+            flag = torch.tensor([1 if parity.get("ok") else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity["ok_all_ranks"] = bool(flag.item())
+            parity["ok"] = parity["ok"] and parity["ok_all_ranks"]
+        if not parity["ok"]:
+            if rank == 0:
+                emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity": parity,
+                      "error": "parity against the reference's configs[0] samples FAILED; nothing was timed"})
+            finish(1)
+            return
+
     cfg = dict(FULL_360P)
     if args.video_layers is not None:
         cfg["visual_layers"] = args.video_layers
@@ -363,51 +348,59 @@ def run_b200_arm(args):
     if args.res == "720p":  # BASELINE.json configs[3]: 720x1280 -> token grid (f, 45, 80), L_v = 176400 at 193 frames
         cfg["grid_size"] = (cfg["grid_size"][0], 45, 80)
     full = (cfg == FULL_360P)
-
-    step_api_error = None
-    want_step_api = os.environ.get("MOVA_BENCH_STEP_API", "1") != "0"
-    try:
-        pipe = build_model(cfg, device, with_step=want_step_api)
-    except Exception as exc:  # the forward-level measurement must not depend on the step wrapper
-        if not want_step_api:
-            raise
-        step_api_error = f"build: {exc!r}"[:300]
-        pipe = build_model(cfg, device, with_step=False)
+    experts = args.experts if args.experts is not None else 2
+    pipe = build_model(cfg, device, experts=experts)
     # eager launches by default: graph replay measured within 0.5 % of eager at 1 and 8 GPUs (the GPU, not the host,
     # is the bottleneck), and NCCL communicators captured into a graph can stall process-group teardown
-    use_graph = bool(args.cuda_graph) if args.cuda_graph is not None else False
+    use_graph = bool(args.cuda_graph)
     pipe.mova_b200_cuda_graph = use_graph
-    host = host_inputs(cfg)
-    dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+
+    host = host_step_inputs(cfg)
+    n_lat = STEP_360P["visual_out_dim"]
+    # the model input cat([latents, condition], dim=1) (pipeline_mova.py:416) is ONE persistent fp32 buffer
+    model_input = torch.cat([host["latents"], host["condition"]], dim=1).to(device)
+    lat_view = model_input[:, :n_lat]
+    audio = host["audio_latents"].to(device)
+    lat_next, audio_next = torch.empty_like(lat_view, memory_format=torch.contiguous_format), torch.empty_like(audio)
+    ctx = {w_: host[f"context_{w_}"].to(device) for w_ in ("pos", "neg")}  # uploaded once per video (:404-405)
+    n_sched = max(args.schedule or 0, 50)
+    timesteps, sigmas = flow_match_schedule(n_sched)
+    ts_dev = [timesteps[i].reshape(1).to(device=device, dtype=torch.float32) for i in range(n_sched)]
+    ts_host = [timesteps[i].reshape(1).float().pin_memory() for i in range(n_sched)]
+    sig = [float(x) for x in sigmas] + [0.0]
+    cfg_scale = 5.0
+    counter = [0]
     torch.cuda.synchronize()
 
-    def forward(d, which):
-        return pipe.forward_dual_tower_dit(
-            pipe.video_dit, d["visual_x"], d["audio_x"], d[f"visual_context_{which}"], d[f"audio_context_{which}"],
-            d["visual_t_mod"], d["audio_t_mod"], d["visual_freqs"], d["audio_freqs"], cfg["grid_size"], cfg["video_fps"],
-            cp_mesh=cp_mesh)
+    def one_step(ts, x_in, a_in, lat_in, lat_out, a_out, idx):
+        """2 x inference_single_step + CFG + Euler update of both latents (pipeline_mova.py:416-475)."""
+        kw = dict(visual_dit=pipe.video_dit, visual_latents=x_in, audio_latents=a_in, timestep=ts, audio_timestep=None,
+                  video_fps=cfg["video_fps"], cp_mesh=cp_mesh)
+        pos_v, pos_a = pipe.inference_single_step(context=ctx["pos"], **kw)
+        neg_v, neg_a = pipe.inference_single_step(context=ctx["neg"], **kw)
+        bstep.guided_update(pos_v, neg_v, lat_in, cfg_scale, sig[idx], sig[idx + 1], out=lat_out)
+        bstep.guided_update(pos_a, neg_a, a_in, cfg_scale, sig[idx], sig[idx + 1], out=a_out)
 
     def step_resident():
-        outs = []
-        for which in ("pos", "neg"):
-            outs.append(forward(dev, which))
-        return outs
+        i = counter[0] % n_sched
+        counter[0] += 1
+        # a new timestep every step, as in the scheduler loop; the updated latents go to a second buffer so that every
+        # timed step sees the same inputs
+        one_step(ts_dev[i], model_input, audio, lat_view, lat_next, audio_next, i)
 
-    out_host = None
+    out_host = [torch.empty(lat_next.shape, dtype=torch.float32).pin_memory(),
+                torch.empty(audio_next.shape, dtype=torch.float32).pin_memory()]
 
     def step_e2e():
-        nonlocal out_host
-        d = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-        outs = []
-        for which in ("pos", "neg"):
-            outs.append(forward(d, which))
-        if out_host is None:
-            out_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in pair] for pair in outs]
+        i = counter[0] % n_sched
+        counter[0] += 1
+        lat_view.copy_(host["latents"], non_blocking=True)          # H2D: this step's fp32 latents ...
+        audio.copy_(host["audio_latents"], non_blocking=True)
+        ts = ts_host[i].to(device, non_blocking=True)               # ... and its timestep
+        one_step(ts, model_input, audio, lat_view, lat_next, audio_next, i)
         if rank == 0:  # the result is replicated across the cp ranks: one host copy, on the reporting rank
-            for pair, hpair in zip(outs, out_host):
-                for t, ht in zip(pair, hpair):
-                    ht.copy_(t, non_blocking=True)
-        return outs
+            out_host[0].copy_(lat_next, non_blocking=True)          # D2H: the updated latents
+            out_host[1].copy_(audio_next, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -428,82 +421,65 @@ def run_b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    launches0 = _lib.LAUNCHES
-    step_resident()  # first warm-up step: in graph mode this one captures the graph
-    launches_per_step = _lib.LAUNCHES - launches0
-    if use_graph:  # capture = 2 eager warm-ups + 1 recorded pass of ONE forward; a step replays it twice
-        launches_per_step = (launches_per_step // 3) * FORWARDS_PER_STEP
-    for _ in range(args.warmup - 1):
+    if args.schedule:
+        run_schedule(args, pipe, cfg, host, ctx, cp_mesh, device, world, rank, timed, parity, full)
+        finish(0)
+        return
+
+    for _ in range(args.warmup):  # the first one fills the prompt memos (text embedding, per-layer text k / v)
         step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    launches0 = _lib.LAUNCHES
     if not use_graph:
         _lib._TIMERS = []  # per-launch CUDA events around every attention kernel of the timed region
     ms_total = timed(step_resident, args.steps)
-    launches = launches_per_step * args.steps
     attn_events, _lib._TIMERS = _lib._TIMERS, None
+    launches = _lib.LAUNCHES - launches0
     clocks = sampler.stop() if rank == 0 else None
     roofline_pass = "CUDA events around every video self-attention launch inside the timed region"
+    eager_ms = None
     if use_graph:
         # events cannot be recorded inside a replayed graph: time the same launches in one eager step right after
         pipe.mova_b200_cuda_graph = False
         step_resident()
         _lib._TIMERS = []
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_resident()
-        e1.record()
-        barrier()
+        eager_ms = timed(step_resident, 1)
         attn_events, _lib._TIMERS = _lib._TIMERS, None
-        eager_ms = e0.elapsed_time(e1)
         pipe.mova_b200_cuda_graph = True
         roofline_pass = ("CUDA events around every video self-attention launch of one EAGER step run right after the "
                          "timed (graph-replay) region; eager step %.1f ms" % eager_ms)
 
     # dominant kernel: video self-attention launches inside the timed region
-    heads_local = cfg["visual_heads"] // world if world > 1 else cfg["visual_heads"]
     f, h, w = cfg["grid_size"]
     L_v = f * h * w
-    sel = [(e0.elapsed_time(e1), 4.0 * b * hh * sq * skv * dd) for (e0, e1, b, sq, skv, hh, dd) in attn_events
+    sel = [(e0.elapsed_time(e1), 4.0 * b * hh * sq * skv * dd) for (e0, e1, b, sq, skv, hh, dd) in (attn_events or [])
            if sq == L_v and skv == L_v]
-    del heads_local
     peaks = measured_peaks()
     roofline = None
     if sel:
         avg_ms = sum(t for t, _ in sel) / len(sel)
         tf = sel[0][1] / (avg_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "attn_traffic.json")
-        if world == 1 and os.path.exists(tpath):  # the ncu capture is of the 40-head single-GPU launch
+        if world == 1 and full and os.path.exists(tpath):  # the ncu capture is of the 40-head single-GPU launch
             with open(tpath) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
+                tj = json.load(fh)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         roofline = {"bound": "tensor", "kernel": "attn_fwd_kernel (video self-attention, L_v x L_v, %d heads/launch)" % sel_heads(attn_events, L_v),
                     "achieved": tf, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": tf / peaks["sustained"],
                     "peak_kind": f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
                     "frac_of_burst_peak": tf / peaks["burst"], "frac_of_nominal_2250": tf / 2250.0,
                     "launches_timed": len(sel), "avg_launch_ms": avg_ms,
                     "share_of_step": sum(t for t, _ in sel) / (eager_ms if use_graph else ms_total),
-                    "how": roofline_pass,
-                    "traffic": traffic}
+                    "how": roofline_pass, "traffic": traffic, "traffic_source": traffic_src}
 
-    # end to end through the public API with host buffers (H2D of the step's inputs, D2H of its outputs)
-    for _ in range(1):
-        step_e2e()
+    # end to end through the public step API with HOST buffers: H2D of the step's latents + timestep, D2H of the result
+    step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    h2d = sum(nbytes(v) for v in host.values())
-    d2h = sum(nbytes(t) for pair in out_host for t in pair)
-
-    # ... and through the step-level public API, the call MOVA.__call__ makes (pipeline_mova.py:429-456):
-    # latents / prompt embeddings / timestep from pinned host memory in, denoised latents out.  Measured last and
-    # guarded: a failure here is reported in the line and leaves every number above untouched.
-    e2e_step = None
-    if want_step_api and step_api_error is None:
-        try:
-            e2e_step = measure_step_api(pipe, cfg, device, cp_mesh, rank, args.steps, timed, lambda: _lib.LAUNCHES)
-        except Exception as exc:
-            step_api_error = repr(exc)[:300]
+    h2d = nbytes(host["latents"]) + nbytes(host["audio_latents"]) + nbytes(ts_host[0])
+    d2h = sum(nbytes(t) for t in out_host)
 
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -513,55 +489,97 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": ("MOVA-360p full dual-tower DiT denoising step: 2 CFG forwards x (40 video blocks "
-                                    "5120/40h/ffn13824 + 30 audio blocks 1536/12h/ffn8960 + 30 bidirectional bridge "
-                                    "layers), L_v=43120 (352x640x193f), L_a=403, 512 text tokens, random init")
+            "config": {"workload": ("MOVA-360p full dual-tower DiT denoising step (BASELINE configs[1]; configs[2]'s step "
+                                    "when cp_size > 1): 2 x inference_single_step [embeddings, patchify, 40 video "
+                                    "blocks 5120/40h/ffn13824 + 30 audio blocks 1536/12h/ffn8960 + 30 bidirectional "
+                                    "bridge layers, head, unpatchify] + CFG + Euler update of both latents; L_v=43120 "
+                                    "(352x640x193f), L_a=403, 512 text tokens, random init")
                        if full else f"NOT the headline config (debug / BASELINE configs[3]): {cfg}",
                        "cp_size": world, "parallelism": f"cp{world}" if world > 1 else "single GPU",
+                       "video_experts_resident": experts,
                        "launch_mode": "cuda graph replay" if use_graph else "eager",
                        "l2_policy": "inputs+weights (~36 GB touched per forward) far exceed the 126 MB L2; no flush needed",
                        "tflop_per_step": flops_step / 1e12},
             "model_tflops": flops_step / (ms_step * 1e-3) / 1e12,
             "model_flops_frac_of_sustained_peak": flops_step / (ms_step * 1e-3) / 1e12 / (peaks["sustained"] * world),
             "clocks": clocks,
+            "parity": parity,
             "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "api": "2 x pipe.forward_dual_tower_dit (pipeline_mova.py:612-711 drop-in): token-level hidden "
-                           "states, contexts, t_mod and RoPE tables from pinned host memory in, hidden states out"},
+                    "api": "2 x pipe.inference_single_step (pipeline_mova.py:500-609 drop-in) + step.guided_update "
+                           "(CFG + FlowMatchPairScheduler.step_from_to): fp32 latents + timestep from pinned host "
+                           "memory in, updated fp32 latents out; prompt embeddings resident (uploaded once per video)"},
             "gpu_launches": launches,
             "roofline": roofline,
         }
-        if e2e_step is not None:
-            # the headline end-to-end number is the call a user of the reference makes per scheduler iteration
-            line["e2e_forward_api"] = line["e2e"]
-            line["e2e"] = e2e_step
-        if step_api_error is not None:
-            line["e2e_step_api_error"] = step_api_error
         if world == 1 and not args.no_cpu_baseline:
             run, scale, cores = cpu_sample_runner()
-            run()  # warm-up (thread pool, allocator)
             sec = run()
-            line["cpu_baseline"] = {"value": 1.0 / (sec * scale), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": CPU_SAMPLE_TEXT, "sample_seconds": sec}
+            line["cpu_baseline"] = cpu_baseline_object(sec, scale, cores)
         emit(line)
-    if world == 1 and step_api_error is not None:  # a failed launch leaves a sticky context error: skip teardown
+    if use_graph and world > 1:
+        # a communicator that was captured into a CUDA graph can block in destroy_process_group(); the line is
+        # printed, so leave without tearing NCCL down
+        dist.barrier()
+        torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
-    if world > 1:
-        if step_api_error is not None:  # the device / communicator may be unusable: the line is out, leave
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
-        dist.barrier()
-        torch.cuda.synchronize()
-        if use_graph:
-            # a communicator that was captured into a CUDA graph can block in destroy_process_group(); the line is
-            # printed and every rank has passed the barrier, so leave without tearing NCCL down
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+    finish(0)
+
+
+def run_schedule(args, pipe, cfg, host, ctx, cp_mesh, device, world, rank, timed, parity, full):
+    """BASELINE configs[2]: the whole denoising loop of MOVA.__call__ (pipeline_mova.py:405-487) through
+    ``dualforce_b200.step.denoising_loop`` -- N scheduler iterations, expert switch at boundary_ratio 0.9 included --
+    timed as one region."""
+    import torch
+
+    from dualforce_b200 import _lib
+    from dualforce_b200 import step as bstep
+
+    n = args.schedule
+    timesteps, sigmas = flow_match_schedule(n)
+    train_t, train_s = flow_match_schedule(1000)
+    pairs = torch.stack([timesteps, timesteps], dim=1)
+
+    def timestep_to_sigma(t):  # FlowMatchPairScheduler.timestep_to_sigma (flow_match_pair.py:208-211)
+        return float(train_s[torch.argmin((train_t - float(t)).abs())])
+
+    boundary = 0.9 * 1000
+
+    def pick(t):  # pipeline_mova.py:406-415
+        return pipe.video_dit_2 if (pipe.video_dit_2 is not None and t < boundary) else pipe.video_dit
+
+    lat, cond, aud = (host[k].to(device) for k in ("latents", "condition", "audio_latents"))
+    res = {}
+
+    def loop(pr):
+        res["out"] = bstep.denoising_loop(pipe, lat, cond, aud, ctx["pos"], ctx["neg"], pr, timestep_to_sigma,
+                                          cfg["video_fps"], cfg_scale=5.0, cp_mesh=cp_mesh, pick_visual_dit=pick)
+
+    loop(pairs[:2])  # warm-up: memos, NCCL channels
+    if pipe.video_dit_2 is not None:
+        loop(pairs[-1:])  # and the second expert's packed weights
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.LAUNCHES
+    ms = timed(lambda: loop(pairs), 1)
+    launches = _lib.LAUNCHES - l0
+    clocks = sampler.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(res["out"][0]).all()) and bool(torch.isfinite(res["out"][1]).all())
+    if rank == 0:
+        flops_step = FORWARDS_PER_STEP * flops_forward(cfg)
+        emit({"metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": n, "warmup": 3,
+              "ms_per_step": ms / n, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+              "data": "synthetic",
+              "config": {"workload": (f"BASELINE configs[2]: MOVA-360p full {n}-step denoising schedule (shift-5 flow-match "
+                                      "sigmas, cfg 5, expert switch at 0.9) through step.denoising_loop, timed as one region")
+                         if full else f"NOT the headline config: {cfg}, {n}-step schedule",
+                         "cp_size": world, "video_experts_resident": 2 if pipe.video_dit_2 is not None else 1,
+                         "tflop_per_step": flops_step / 1e12, "schedule_seconds": ms * 1e-3},
+              "model_tflops": flops_step * n / (ms * 1e-3) / 1e12, "clocks": clocks, "parity": parity,
+              "outputs_finite": finite, "gpu_launches": launches})
 
 
 def sel_heads(events, L_v):
@@ -604,8 +622,12 @@ def main():
     ap.add_argument("--res", choices=["360p", "720p"], default="360p",
                     help="720p = BASELINE.json configs[3] (L_v = 176400; meant for --gpus 8); marks the line REDUCED/other")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cuda-graph", type=int, default=None,
+    ap.add_argument("--cuda-graph", type=int, default=0,
                     help="1: replay the forward as a CUDA graph, 0: eager launches (default)")
+    ap.add_argument("--no-parity", action="store_true", help="debug: skip the configs[0] parity gate")
+    ap.add_argument("--experts", type=int, default=None, help="resident video experts (default 2, as in the reference)")
+    ap.add_argument("--schedule", type=int, default=0,
+                    help="BASELINE configs[2]: time the whole N-step denoising loop (step.denoising_loop) as one region")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -70,10 +70,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on a barrier that lives in another CTA of the cluster (address from mapa_shared)
+// arrive on a barrier that lives in another CTA of the cluster (address from mapa_shared).  Default semantics
+// (.release at CTA scope): the explicit `.release.cluster` form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in
+// front of the arrive -- measured as ~90 % of the peer producer's time in the CTA-pair GEMM (profiles/r02).  What the
+// consumers order against is tcgen05 / TMA state, fenced separately (tcgen05.fence, complete_tx), not generic memory.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)

@@ -101,7 +101,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (threadIdx.x == 32) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(full_bar(s), CG);  // CG=2: leader's expect_tx arrive + peer's remote arrive
+      // one arrival: the leader's expect_tx covering BOTH CTAs' bytes.  The peer only issues its TMA loads against the
+      // leader's barrier; their complete_tx may land before the expect_tx (the tx-count is signed within a phase) but
+      // never in an earlier phase: the peer waits for its multicast `empty` first, i.e. after the leader's MMAs consumed
+      // the stage, so the leader's barrier is already in the next phase with its own arrival still pending.
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);  // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -146,7 +150,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             const uint32_t leader_full = mapa_shared(full_bar(stage), 0);
             if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-            else mbar_arrive_cluster(leader_full);
             tma_load_3d_pair(sA, &tmA, leader_full, k_in_seg, row0, seg);
             tma_load_2d_pair(sB, &tmB, leader_full, kb * GEMM_BK, col0);
           }

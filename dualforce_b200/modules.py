@@ -81,6 +81,22 @@ def _kv_splits(n_queries: int, n_keys: int) -> int:
     return want
 
 
+def param_sig(*tensors) -> tuple:
+    """(pointer, version) of every tensor: a cache key that changes when a parameter is moved OR updated in place
+    (``load_state_dict`` / ``copy_`` bump ``_version``; views of a packed buffer share the buffer's counter)."""
+    sig = []
+    for t in tensors:
+        if t is None:
+            sig.append(None)
+            continue
+        try:
+            ver = t._version
+        except RuntimeError:  # inference-mode tensor: immutable
+            ver = -1
+        sig.append((t.data_ptr(), ver))
+    return tuple(sig)
+
+
 class _Packed:
     """Lazily built packed weights, rebuilt if the owning parameters moved (``.to()``, ``.cuda()``, dtype cast)."""
 
@@ -197,7 +213,7 @@ class CrossAttention(nn.Module):
                 version = y._version
             except RuntimeError:  # inference-mode tensor
                 version = -1
-            key = (y.data_ptr(), tuple(y.shape), version, w.data_ptr())
+            key = (y.data_ptr(), tuple(y.shape), version) + param_sig(w, b, self.norm_k.weight)
             memo = self.__dict__.setdefault("_kv_memo", {})
             hit = memo.get(key)
             if hit is not None:

@@ -19,7 +19,7 @@ import torch
 
 from . import cp as cpmod
 from . import ops, rope
-from .modules import ConditionalCrossAttentionBlock, DiTBlock, DualTowerConditionalBridge
+from .modules import ConditionalCrossAttentionBlock, DiTBlock, DualTowerConditionalBridge, param_sig
 
 __all__ = ["forward_dual_tower_dit", "install", "swap_modules", "CPRuntime", "GraphedForward"]
 
@@ -56,15 +56,20 @@ _RUNTIMES = {}
 
 
 def _cp_weights(block: DiTBlock, plan: cpmod.UlyssesPlan):
-    """Destination-rank-major copies of the self-attention weights of ``block`` for ``plan`` (built once)."""
+    """Destination-rank-major copies of the self-attention weights of ``block`` for ``plan``: built once per
+    (plan, parameter pointers AND versions) -- ``load_state_dict`` / ``copy_`` / an in-place LoRA merge after the first
+    context-parallel forward bump the versions and force a rebuild.  Cost: a second copy of Wq|Wk|Wv|Wo per video block
+    (4 d^2 bf16 = 210 MB at d = 5120, 8.4 GB per 40-layer tower) while cp > 1; one entry per block, replaced when cp
+    changes."""
     cache = getattr(block, "_cp_cache", None)
     if cache is None:
         cache = block._cp_cache = {}
-    key = (plan.cp, plan.groups, block.self_attn.q.weight.data_ptr())
+    sa = block.self_attn
+    key = (plan.cp, plan.groups) + param_sig(sa.q.weight, sa.k.weight, sa.v.weight, sa.o.weight, sa.q.bias, sa.k.bias,
+                                             sa.v.bias, sa.norm_q.weight, sa.norm_k.weight)
     hit = cache.get(key)
     if hit is not None:
         return hit
-    sa = block.self_attn
     dev = sa.q.weight.device
     rows = plan.qkv_row_index().to(dev)
     chan = plan.channel_index().to(dev)
@@ -325,8 +330,23 @@ def forward_dual_tower_dit(self, visual_dit, visual_x: torch.Tensor, audio_x: to
                    visual_t_mod=visual_t_mod, audio_t_mod=audio_t_mod, visual_freqs=visual_freqs, audio_freqs=audio_freqs)
     if not getattr(self, "mova_b200_cuda_graph", False):
         return _forward_eager(self, visual_dit, **tensors, **statics, cp_mesh=cp_mesh)
+    if any(hasattr(m, "_hf_hook") for m in (visual_dit, self.audio_dit, self.dual_tower_bridge)):
+        raise RuntimeError("dualforce_b200: cuda_graph=True bakes weight pointers into the graph; it cannot be combined "
+                           "with accelerate CPU-offload hooks (weights move between forwards)")
+    # a captured graph holds raw pointers: scales must be plain floats BEFORE capture (a 0-dim Parameter would need
+    # .item(), a host sync that aborts capture), and the key must change when the weights move
+    bridge = self.dual_tower_bridge
+    for name in ("condition_scale", "a2v_condition_scale", "v2a_condition_scale"):
+        if isinstance(statics[name], torch.Tensor):
+            statics[name] = bridge._scale(statics[name])
+    if statics["condition_scale"] is None or isinstance(bridge.condition_scale, torch.Tensor):
+        statics["condition_scale"] = bridge._scale(statics["condition_scale"])
+    blocks = visual_dit.blocks
+    a2v = list(bridge.audio_to_video_conditioners.values())
+    weights_sig = param_sig(blocks[0].self_attn.q.weight, blocks[len(blocks) - 1].ffn[2].weight,
+                            self.audio_dit.blocks[0].self_attn.q.weight, a2v[0].inner.q.weight if a2v else None)
     cache = self.__dict__.setdefault("_mova_b200_graphs", {})
-    key = (id(visual_dit), id(cp_mesh), tuple(sorted(statics.items())),
+    key = (id(visual_dit), id(cp_mesh), tuple(sorted((k, v) for k, v in statics.items())), weights_sig,
            tuple((k, tuple(v.shape), v.dtype, str(v.device)) for k, v in tensors.items()))
     runner = cache.get(key)
     if runner is None:

@@ -36,7 +36,7 @@ import torch.nn as nn
 
 from . import cp as cpmod
 from . import ops, rope
-from .modules import DiTBlock
+from .modules import DiTBlock, param_sig
 
 __all__ = ["Head", "WanModel", "WanAudioModel", "inference_single_step", "embed_time", "embed_text", "patchify",
            "head_unpatchify", "guided_update", "denoising_loop", "clear_step_caches"]
@@ -256,7 +256,7 @@ def embed_time(model, timestep: torch.Tensor) -> Tuple[torch.Tensor, torch.Tenso
         raise NotImplementedError("one timestep per call (MOVA runs B = 1)")
     memo = _memo(model, "_mova_b200_time", 2)
     te, tp = model.time_embedding, model.time_projection
-    key = _tensor_key(timestep) + (te[0].weight.data_ptr(),)
+    key = _tensor_key(timestep) + param_sig(te[0].weight, te[0].bias, te[2].weight, te[2].bias, tp[1].weight, tp[1].bias)
     hit = memo.get(key)
     if hit is not None:
         return hit
@@ -274,7 +274,7 @@ def embed_text(model, context: torch.Tensor) -> torch.Tensor:
     Memoised per context tensor; the result is flagged so each block may memoise its text k / v on it."""
     memo = _memo(model, "_mova_b200_text", 4)
     te = model.text_embedding
-    key = _tensor_key(context) + (te[0].weight.data_ptr(),)
+    key = _tensor_key(context) + param_sig(te[0].weight, te[0].bias, te[2].weight, te[2].bias)
     hit = memo.get(key)
     if hit is not None:
         return hit

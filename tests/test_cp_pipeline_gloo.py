@@ -79,7 +79,17 @@ def _worker(rank, world, port, grid, heads, results):
         chunk, chunk_len, pad_len, total = cp._sp_split_tensor(tab, sp_size=world, sp_rank=rank)
         sp_ok = bool(torch.equal(cp._sp_all_gather_avg(chunk, sp_group=None, pad_len=pad_len), tab)
                      and (chunk_len, pad_len, total) == ((4, 1, 7) if world == 2 else (2, 1, 7)))
-        results[rank] = dict(sp_ok=sp_ok, 
+        # weights reloaded in place after a context-parallel forward: the permuted CP copies must follow
+        Qv, Qa, Qb, _ = O.make_step_case(cfg, 78)
+        Qv, Qa, Qb = bf16_round(Qv), bf16_round(Qa), bf16_round(Qb)
+        vis.load_state_dict({k: v.to(torch.bfloat16) for k, v in Qv.items()})
+        aud.load_state_dict({k: v.to(torch.bfloat16) for k, v in Qa.items()})
+        bridge.load_state_dict({k: v.to(torch.bfloat16) for k, v in Qb.items()})
+        v3, a3 = pipe.inference_single_step(**kw, cp_mesh=mesh)
+        vis_f, aud_f, bridge_f, pipe_f = build_step_towers(cfg, Qv, Qa, Qb, device="cpu")
+        v4, a4 = pipe_f.inference_single_step(**dict(kw, visual_dit=vis_f), cp_mesh=mesh)
+        reload_ok = bool(torch.equal(v3, v4) and torch.equal(a3, a4) and not torch.equal(v3, v2))
+        results[rank] = dict(sp_ok=sp_ok, reload_ok=reload_ok,
             cp_vs_oracle_v=metrics(v2, rv), cp_vs_oracle_a=metrics(a2, ra), cp_vs_cp1_v=metrics(v2, v1.float()),
             cp_vs_cp1_a=metrics(a2, a1.float()), shapes=(tuple(v2.shape), tuple(a2.shape), tuple(full_v.shape)),
             calls=calls, v2=v2.float(), a2=a2.float())
@@ -109,6 +119,7 @@ def test_step_context_parallel_gloo(world, grid, heads):
         # v2a merges partial attentions: one lse_merge per bridge layer
         assert r["calls"]["lse_merge"] == 2
         assert r["sp_ok"]
+        assert r["reload_ok"], "stale context-parallel weight copies after load_state_dict"
     # every rank ends with the same full-length outputs
     for rank in range(1, world):
         assert torch.equal(results[0]["v2"], results[rank]["v2"]) and torch.equal(results[0]["a2"], results[rank]["a2"])

@@ -1,14 +1,13 @@
 """-m gpu: BASELINE.json configs[0] on the CUDA path -- MOVA-360p widths (5120 / 40 heads / ffn 13824 and 1536 / 12 /
 8960), 2 + 2 blocks, 2 bridge layers, L_v = 4400, L_a = 36, 512 text tokens -- against sampled outputs of the REFERENCE
-itself (fp32 weights, fp32 CPU; tests/golden/reduced_360p_samples.npz).  The kernels are the shipped, parity-green
-ones; the test is new and has not run on hardware yet, hence the non-strict xfail."""
+itself (fp32 weights, fp32 CPU; tests/golden/reduced_360p_samples.npz)."""
 import pytest
 import torch
 
 from test_oracle_golden import load_reduced_case
 from util import build_towers, metrics, to_dev
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_reduced_360p_forward_vs_reference_samples():

@@ -1,12 +1,11 @@
 """-m gpu: size-independent properties at the MOVA-720p geometry (BASELINE.json configs[3]: L_v = 49 x 45 x 80 =
-176 400 video tokens) -- the largest sequence the path is specified for.  Not yet run on hardware (written after the
-round's GPU budget was spent), hence the non-strict xfail; the kernels involved are the shipped, parity-green ones."""
+176 400 video tokens) -- the largest sequence the path is specified for (green on B200 since round 1)."""
 import pytest
 import torch
 
 from util import metrics
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run at 720p sizes pending")]
+pytestmark = [pytest.mark.gpu]
 
 S = 49 * 45 * 80
 

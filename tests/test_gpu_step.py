@@ -2,10 +2,8 @@
 and ``inference_single_step`` through the C ABI, against the CPU oracle, the reference's golden outputs
 (tests/golden/tiny_step.npz) and, at BASELINE.json sizes, exact index round trips.
 
-Written after this round's GPU budget was spent: the host logic is verified on CPU (tests/test_host_emulated.py,
-tests/test_cp_pipeline_gloo.py run the same Python with the kernels emulated), but the kernels of step.cu have not
-executed on hardware yet, hence the non-strict xfail mark -- XPASS on the B200 box is the expected outcome; drop the
-mark then."""
+The host logic is also verified on CPU (tests/test_host_emulated.py, tests/test_cp_pipeline_gloo.py run the same
+Python with the kernels emulated); every test here passed on B200 at the end of round 1 (GPUTEST_r01.json)."""
 import math
 import os
 import socket
@@ -19,9 +17,7 @@ import mova_oracle as O
 from test_oracle_step_golden import load_step_case
 from util import assert_close, bf16_round, build_step_towers
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (GPU budget of the round exhausted "
-                                                     "before csrc/step.cu existed); verified on CPU with emulated kernels")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

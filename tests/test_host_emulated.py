@@ -168,6 +168,30 @@ def test_step_memoises_prompt_and_timestep_work(emu, step_case):
     assert c4["linear"] == c_pos1["linear"] and not torch.equal(v4, v2)
 
 
+def test_weight_reload_invalidates_every_memo(emu, step_case):
+    """load_state_dict() after a step keeps every data_ptr (the packed buffers are updated in place) but bumps the
+    parameter versions: time / text embeddings, per-layer text k / v and the packed weights must all follow.  A step
+    on reloaded towers is bit-identical to the same step on towers built from the new weights."""
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    ctx = inp["context"].to(torch.bfloat16)
+    kw = dict(visual_latents=inp["visual_latents"], audio_latents=inp["audio_latents"], context=ctx,
+              timestep=inp["timestep"], audio_timestep=None, video_fps=cfg["video_fps"])
+    v_old, a_old = pipe.inference_single_step(visual_dit=vis, **kw)
+    Qv, Qa, Qb, _ = O.make_step_case(cfg, 4242)
+    Qv, Qa, Qb = bf16_round(Qv), bf16_round(Qa), bf16_round(Qb)
+    ptr = vis.blocks[0].self_attn.q.weight.data_ptr()
+    vis.load_state_dict({k: v.to(torch.bfloat16) for k, v in Qv.items()})
+    aud.load_state_dict({k: v.to(torch.bfloat16) for k, v in Qa.items()})
+    bridge.load_state_dict({k: v.to(torch.bfloat16) for k, v in Qb.items()})
+    assert vis.blocks[0].self_attn.q.weight.data_ptr() == ptr  # in place: only the version tells
+    v_new, a_new = pipe.inference_single_step(visual_dit=vis, **kw)
+    vis2, aud2, bridge2, pipe2 = build_step_towers(cfg, Qv, Qa, Qb, device="cpu")
+    v_ref, a_ref = pipe2.inference_single_step(visual_dit=vis2, **kw)
+    assert torch.equal(v_new, v_ref) and torch.equal(a_new, a_ref)
+    assert not torch.equal(v_new, v_old)
+
+
 def test_twin_state_dict_keys_equal_the_reference(step_case):
     cfg, Pv, Pa, Pb, inp, gold, meta = step_case
     vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
