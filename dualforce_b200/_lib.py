@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmova_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/mova_b200.h one to one
 SIGNATURES = {
@@ -35,13 +35,11 @@ SIGNATURES = {
         [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
          c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     ),
-    "mova_b200_attn_fwd_ex": (
+    "mova_b200_attn_fwd_variant": (
         c_int,
         [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
-         c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p],
+         c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p],
     ),
-    "mova_b200_head_norms": (
-        c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mova_b200_lse_merge": (
         c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mova_b200_layernorm": (

@@ -1,3 +1,7 @@
+// Round-1 schedule of the attention forward (two 128-row query tiles per CTA, S/P aliased per tile), kept as variant
+// 3 of mova_b200_attn_fwd_variant for A/B measurements against the round-2 kernel in attn_pair.cu, which is what
+// mova_b200_attn_fwd runs.  Also home of the C-ABI entry points of both.
+//
 // Non-causal softmax attention forward on tcgen05, head_dim 128:  O = softmax(Q K^T * scale) V.
 //
 // Replaces flash_attention() (mova/diffusion/models/wan_video_dit.py:58-91) at its three call sites:
@@ -47,8 +51,7 @@ constexpr int AT_BAR_KVEMPTY = AT_BAR_KVFULL + AT_NS;  // [NS]
 constexpr int AT_BAR_SFULL = AT_BAR_KVEMPTY + AT_NS;   // [2]
 constexpr int AT_BAR_PREADY = AT_BAR_SFULL + 2;        // [tile][half of the key block] = [4]
 constexpr int AT_BAR_ODONE = AT_BAR_PREADY + 4;        // [2]
-constexpr int AT_BAR_SLOADED = AT_BAR_ODONE + 2;       // [2] (QSPLIT > 0: softmax has the score tile in registers)
-constexpr int AT_NUM_BARS = AT_BAR_SLOADED + 2;
+constexpr int AT_NUM_BARS = AT_BAR_ODONE + 2;
 constexpr int AT_OFF_TMEM_PTR = AT_OFF_BARS + AT_NUM_BARS * 8;
 constexpr int AT_SMEM_BYTES = AT_OFF_TMEM_PTR + 16;
 static_assert(AT_SMEM_BYTES <= 232448, "attention shared memory budget exceeded");
@@ -57,25 +60,8 @@ constexpr uint32_t AT_TMEM_S = 0;    // + 128 * tile
 constexpr uint32_t AT_TMEM_O = 256;  // + 128 * tile
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 constexpr int AT_DEFAULT_EMU = 4;
-// BOUNDED: P = 2^(s - m) may grow to 2^64; the fp32 accumulators then stay below 2^64 * 2^18 keys * |v| << 2^127
-constexpr float AT_BOUND_SLACK = 64.0f;
-
 // EMU: how many of every 16 score pairs take the polynomial path (0 = all MUFU, 8 = half and half)
-// QSPLIT (experimental, MOVA_ATTN_VARIANT=v7 / v8; 0 = the shipped v3 schedule): Q.K^T of block j+1 is issued in
-// N-slices so that only the slice that overwrites the last-consumed part of P(j) stays on the critical path:
-//   keys 64..127 -> columns 64..127, which hold no P: issued as soon as the softmax warps have S(j) in registers
-//                   (new barrier SLOADED), i.e. it runs in what used to be tensor-pipe idle time;
-//   keys 0..63   -> columns 0..63 (= P): QSPLIT 1: one N=64 slice after P.V(j);
-//                   QSPLIT 2: keys 0..31 after the first half of P.V(j), keys 32..63 after the second.
-// tcgen05.mma cost is linear in N (floor 128*N/256 cycles per K=16 step), so the tensor work is unchanged while the
-// dependent chain  P(j) ready -> S(j+1) ready  shrinks from P.V half + 512 cycles to P.V half + 256 (128) cycles.
-// BOUNDED (experimental, MOVA_ATTN_BOUNDED=1): the row maximum is only needed as a reference point that keeps
-// exp2(s - m) inside the fp32 range; softmax itself is invariant to it.  With |q_i| per query row and max_j |k_j| per
-// 128-key block supplied (mova_b200_head_norms), Cauchy-Schwarz gives an upper bound of every score of the block; while
-// that bound stays within 2^AT_BOUND_SLACK of the reference point already in use, the 128-element max reduction and
-// the rescale vote (about a quarter of the softmax time per block) are skipped.  When the bound is not good enough
-// the block takes the exact path below, so the result never depends on the inputs being "nice".
-template <int EMU, bool TRACE, int QSPLIT, bool BOUNDED>
+template <int EMU, bool TRACE>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -117,7 +103,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(bar(AT_BAR_PREADY + 2 * i), 4);  // one arrive per softmax warp
       mbar_init(bar(AT_BAR_PREADY + 2 * i + 1), 4);
       mbar_init(bar(AT_BAR_ODONE + i), 1);
-      mbar_init(bar(AT_BAR_SLOADED + i), 4);
     }
     fence_barrier_init();
   }
@@ -140,18 +125,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int tail = p.Skv - (n_kv - 1) * 128;  // valid keys of the last block, 1..128
       float m_used = -INFINITY;  // maximum (raw score units) the running O and l are expressed against
       float l = 0.f;
-      float qn_c = 0.f;                 // BOUNDED: |q_row| * scale * log2(e), rounded up
-      const float* kmax_row = nullptr;  // BOUNDED: max |k| of every key block of this (b, h)
-      if constexpr (BOUNDED) {
-        const int grow = row_base + tile * 128 + r;
-        if (grow < p.Sq) qn_c = p.qnorm[(static_cast<long long>(b) * p.Sq + grow) * p.H + h] * c * 1.001f;
-        kmax_row = p.kmax + (static_cast<long long>(b) * p.H + h) * n_kv;
-      }
 
 #pragma unroll 1
       for (int j = 0; j < n_kv; ++j) {
-        float kb = 0.f;
-        if constexpr (BOUNDED) kb = __ldg(kmax_row + j);  // in flight while this warp waits for S(j)
         mbar_wait(bar(AT_BAR_SFULL + tile), j & 1);
         tc_fence_after();
         if ((threadIdx.x & 127) == 0) ev(tile, 1);
@@ -159,25 +135,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; ++q) tmem_ld_x32(t_s + q * 32, reinterpret_cast<uint32_t(&)[32]>(s[q * 32]));
         tmem_wait_ld();
-        if constexpr (QSPLIT > 0) {
-          // the score tile is in registers: columns 64..127 may take the upper half of S(j+1)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(AT_BAR_SLOADED + tile));
-        }
         if ((threadIdx.x & 127) == 0) ev(tile, 2);
         if (j == n_kv - 1 && tail < 128) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
             if (i >= tail) s[i] = 0xff800000u;  // -inf
         }
-        bool skip_max = false;
-        if constexpr (BOUNDED) {
-          // every score of this block is <= |q||k_max| (in exp2 units: qn_c * kb); if even that stays within the
-          // slack of the reference point in use, nothing can overflow and the exact maximum is not needed
-          if (j > 0) skip_max = __all_sync(0xffffffffu, fmaf(qn_c, kb, -m_used * c) <= AT_BOUND_SLACK);
-        }
-        if (!skip_max) {
+        {
         // 8 independent chains: the 3-input FMNMX has a long dependent-issue latency (4 chains cost ~420 cycles)
         float mx[8];
 #pragma unroll
@@ -211,7 +175,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_wait_st();
           }
         }
-        }  // !skip_max
+        }
         if ((threadIdx.x & 127) == 0) ev(tile, 3);
         const float neg = -m_used * c;
         const float2 c2 = make_float2(c, c);
@@ -340,21 +304,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         __syncwarp();
       };
-      // S[:, n0 : n0 + N] = Q . K[n0 : n0 + N]^T  (N = 64 or 32): rows n0.. of the K tile start n0 * 128 bytes into
-      // each 64-column swizzle panel (a multiple of the 1024-byte swizzle atom), accumulator columns n0..n0+N-1
-      auto issue_qk_slice = [&](int tile, uint32_t kbase, int n0, uint32_t idesc, bool commit_sfull) {
-        const uint64_t qd = umma_desc_k_sw128(smem_base + AT_OFF_Q + tile * AT_TILE_BYTES);
-        const uint64_t kd = umma_desc_k_sw128(kbase + n0 * 128);
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t off16 = ((ks >> 2) * AT_HALF_BYTES + (ks & 3) * 32) >> 4;
-            umma_ss<1>(tmem_u + AT_TMEM_S + tile * 128 + n0, qd + off16, kd + off16, idesc, ks > 0 ? 1u : 0u);
-          }
-          if (commit_sfull) umma_commit(bar(AT_BAR_SFULL + tile));
-        }
-        __syncwarp();
-      };
       // P.V over keys [64*half, 64*half + 64) of the block
       auto issue_pv_half = [&](int tile, uint32_t vbase, int half, bool acc) {
         const uint64_t vd = umma_desc_mn_sw128(vbase + half * 8192, AT_HALF_BYTES, 1024);
@@ -396,46 +345,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t kslot = slot;
         const uint32_t kphase = phase;
         for (int tile = 0; tile < nt; ++tile) {
-          if constexpr (QSPLIT > 0) {
-            if (!last) {
-              constexpr uint32_t IDESC_QK64 = umma_idesc_bf16(128, 64, 0, 0);
-              if (tile == 0) {
-                mbar_wait(bar(AT_BAR_KVFULL + kslot), kphase);
-                tc_fence_after();
-              }
-              // upper half of S(j+1) into the columns P(j) does not use, as soon as S(j) has been read
-              mbar_wait(bar(AT_BAR_SLOADED + tile), j & 1);
-              tc_fence_after();
-              issue_qk_slice(tile, slot_addr(kslot), 64, IDESC_QK64, false);
-            }
-          }
           // one barrier per half of P: a single two-phase barrier would let the softmax run two phases ahead of
           // this warp, which a parity wait cannot tell apart from "not there yet"
           mbar_wait(bar(AT_BAR_PREADY + 2 * tile), j & 1);
           tc_fence_after();
           if (tile == 0) ev(2, 10); else ev(2, 11);
           issue_pv_half(tile, slot_addr(vslot), 0, j > 0);
-          if constexpr (QSPLIT == 2) {
-            // keys 0..31 overwrite the half of P the MMAs just issued consume (the tensor pipe runs in issue order)
-            if (!last) issue_qk_slice(tile, slot_addr(kslot), 0, umma_idesc_bf16(128, 32, 0, 0), false);
-          }
           mbar_wait(bar(AT_BAR_PREADY + 2 * tile + 1), j & 1);
           tc_fence_after();
           issue_pv_half(tile, slot_addr(vslot), 1, true);
           if (tile == 0) ev(2, 12); else ev(2, 13);
           if (last) commit(bar(AT_BAR_ODONE + tile));
           if (!last) {
-            if constexpr (QSPLIT == 0) {
-              if (tile == 0) {
-                mbar_wait(bar(AT_BAR_KVFULL + kslot), kphase);
-                tc_fence_after();
-              }
-              issue_qk(tile, slot_addr(kslot));
-            } else if constexpr (QSPLIT == 1) {
-              issue_qk_slice(tile, slot_addr(kslot), 0, umma_idesc_bf16(128, 64, 0, 0), true);
-            } else {
-              issue_qk_slice(tile, slot_addr(kslot), 32, umma_idesc_bf16(128, 32, 0, 0), true);
+            if (tile == 0) {
+              mbar_wait(bar(AT_BAR_KVFULL + kslot), kphase);
+              tc_fence_after();
             }
+            issue_qk(tile, slot_addr(kslot));
             if (tile == 0) ev(2, 14); else ev(2, 15);
           }
         }
@@ -455,10 +381,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp_idx == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
-template <int EMU, bool TRACE, int QSPLIT = 0, bool BOUNDED = false>
+template <int EMU, bool TRACE>
 static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                        const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
-  auto kernel = attn_fwd_kernel<EMU, TRACE, QSPLIT, BOUNDED>;
+  auto kernel = attn_fwd_kernel<EMU, TRACE>;
   static bool configured[64] = {false};
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));
@@ -473,28 +399,37 @@ static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, c
 
 }  // namespace mv
 
+// The schedule mova_b200_attn_fwd runs (chosen from the A/B measurements in profiles/): 92 = CTA-pair kernel
+#ifndef MOVA_ATTN_DEFAULT_VARIANT
+#define MOVA_ATTN_DEFAULT_VARIANT 92
+#endif
+#ifndef MOVA_ATTN_DEFAULT_EMU
+#define MOVA_ATTN_DEFAULT_EMU 4
+#endif
+
 extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs, int64_t k_ss,
                                   const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs, int64_t o_ss,
                                   float* lse, int B, int Sq, int Skv, int H, int D, float softmax_scale,
                                   void* stream) {
-  return mova_b200_attn_fwd_ex(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, o_bs, o_ss, lse, B, Sq, Skv, H, D,
-                               softmax_scale, nullptr, nullptr, stream);
+  return mova_b200_attn_fwd_variant(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, o_bs, o_ss, lse, B, Sq, Skv, H, D,
+                                    softmax_scale, MOVA_ATTN_DEFAULT_VARIANT, MOVA_ATTN_DEFAULT_EMU, nullptr, stream);
 }
 
-extern "C" int mova_b200_attn_fwd_ex(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs,
-                                     int64_t k_ss, const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs,
-                                     int64_t o_ss, float* lse, int B, int Sq, int Skv, int H, int D,
-                                     float softmax_scale, const float* q_norm, const float* k_block_max,
-                                     void* stream) {
+extern "C" int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs,
+                                          int64_t k_ss, const void* v, int64_t v_bs, int64_t v_ss, void* o,
+                                          int64_t o_bs, int64_t o_ss, float* lse, int B, int Sq, int Skv, int H, int D,
+                                          float softmax_scale, int variant, int emu, unsigned long long* trace,
+                                          void* stream) {
   using namespace mv;
-  MV_REQUIRE((q_norm == nullptr) == (k_block_max == nullptr),
-             "mova_b200_attn_fwd_ex: q_norm and k_block_max must come together");
   MV_REQUIRE(q && k && v && o, "mova_b200_attn_fwd: null pointer");
   MV_REQUIRE(D == 128, "mova_b200_attn_fwd: head_dim %d unsupported (the MOVA towers and bridge use 128)", D);
   MV_REQUIRE(B >= 1 && H >= 1 && Sq >= 0 && Skv >= 1, "mova_b200_attn_fwd: bad shape B=%d Sq=%d Skv=%d H=%d", B, Sq,
              Skv, H);
   MV_REQUIRE(B <= 65535 && H <= 65535, "mova_b200_attn_fwd: B and H must fit a grid dimension");
   MV_REQUIRE(softmax_scale > 0.f, "mova_b200_attn_fwd: softmax_scale must be positive");
+  MV_REQUIRE(variant == 3 || variant == 91 || variant == 92, "mova_b200_attn_fwd_variant: variant must be 3 (round-1 "
+             "schedule), 91 (round-2 schedule, single CTA) or 92 (round-2 schedule, CTA pair); got %d", variant);
+  MV_REQUIRE(emu == 0 || emu == 4 || emu == 8, "mova_b200_attn_fwd_variant: emu must be 0, 4 or 8 (got %d)", emu);
   const int64_t row = static_cast<int64_t>(H) * D;
   MV_REQUIRE(q_ss >= row && k_ss >= row && v_ss >= row && o_ss >= row,
              "mova_b200_attn_fwd: sequence stride smaller than H*D");
@@ -507,10 +442,13 @@ extern "C" int mova_b200_attn_fwd_ex(const void* q, int64_t q_bs, int64_t q_ss, 
     v_bs = v_ss * Skv;
   }
 
+  // K box: 128 keys per load, or this CTA's 64 keys of the block in the CTA-pair kernel
+  const uint32_t k_box_rows = (variant == 92) ? 64 : 128;
+  // O box: the round-2 kernels store one 64-column panel per warpgroup
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = encode_tmap_3d(&tmQ, q, row, Sq, B, q_ss, q_bs, 64, 128, 1)) != 0) return rc;
-  if ((rc = encode_tmap_3d(&tmK, k, row, Skv, B, k_ss, k_bs, 64, 128, 1)) != 0) return rc;
+  if ((rc = encode_tmap_3d(&tmK, k, row, Skv, B, k_ss, k_bs, 64, k_box_rows, 1)) != 0) return rc;
   if ((rc = encode_tmap_3d(&tmV, v, row, Skv, B, v_ss, v_bs, 64, 128, 1)) != 0) return rc;
   if ((rc = encode_tmap_3d(&tmO, o, row, Sq, B, o_ss, o_bs, 64, 128, 1)) != 0) return rc;
 
@@ -521,74 +459,16 @@ extern "C" int mova_b200_attn_fwd_ex(const void* q, int64_t q_bs, int64_t q_ss, 
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.lse = lse;
-  p.qnorm = q_norm;
-  p.kmax = k_block_max;
+  p.trace = trace;
 
   debug_attach();
-  // MOVA_ATTN_VARIANT=v6 selects the experimental event-driven kernel of attn_v6.cu (see its header); v7 / v8 the
-  // sliced-QK schedules of this file (QSPLIT 1 / 2, see the kernel's header comment).  Default: v3.
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("MOVA_ATTN_VARIANT");
-    variant = 3;
-    if (e != nullptr && e[0] == 'v' && e[1] >= '6' && e[1] <= '8' && e[2] == 0) variant = e[1] - '0';
-  }
-  // share of exponentials evaluated by polynomial (in 16ths of the pairs); MOVA_ATTN_EMU overrides for tuning
-  static int emu = -1;
-  if (emu < 0) {
-    const char* e = getenv("MOVA_ATTN_EMU");
-    emu = e ? atoi(e) : AT_DEFAULT_EMU;
-  }
-  dim3 grid((Sq + 255) / 256, H, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // diagnostics only: MOVA_ATTN_TRACE=<file> records the event timeline of CTA (0,0,0) of every launch (synchronous!)
-  static const char* trace_path = getenv("MOVA_ATTN_TRACE");
-  p.trace = nullptr;
-  if (trace_path != nullptr) {
-    static unsigned long long* tbuf = nullptr;
-    if (tbuf == nullptr) MV_CHECK_CUDA(cudaMalloc(&tbuf, 3 * 4096 * sizeof(unsigned long long)));
-    MV_CHECK_CUDA(cudaMemsetAsync(tbuf, 0, 3 * 4096 * sizeof(unsigned long long), st));
-    p.trace = tbuf;
-    int rc;
-    if (variant == 7) rc = launch_attn<AT_DEFAULT_EMU, true, 1>(grid, st, tmQ, tmK, tmV, tmO, p);
-    else if (variant == 8) rc = launch_attn<AT_DEFAULT_EMU, true, 2>(grid, st, tmQ, tmK, tmV, tmO, p);
-    else rc = (emu == 0) ? launch_attn<0, true>(grid, st, tmQ, tmK, tmV, tmO, p)
-                         : launch_attn<AT_DEFAULT_EMU, true>(grid, st, tmQ, tmK, tmV, tmO, p);
-    if (rc != 0) return rc;
-    MV_CHECK_CUDA(cudaStreamSynchronize(st));
-    static unsigned long long host[3 * 4096];
-    MV_CHECK_CUDA(cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost));
-    FILE* f = fopen(trace_path, "wb");
-    if (f != nullptr) {
-      fwrite(host, 1, sizeof(host), f);
-      fclose(f);
-    }
-    return 0;
-  }
-  // the experimental schedules come with the polynomial-exp2 share 0 / 25 % / 50 % (MOVA_ATTN_EMU = 0 / 4 / 8): once
-  // the row maximum and part of the MMA chain are off the softmax path, the MUFU unit is the next thing to balance
-#define MV_ATTN_EXP(QS, BND)                                                                        \
-  do {                                                                                              \
-    if (emu == 0) return launch_attn<0, false, QS, BND>(grid, st, tmQ, tmK, tmV, tmO, p);           \
-    if (emu == 8) return launch_attn<8, false, QS, BND>(grid, st, tmQ, tmK, tmV, tmO, p);           \
-    return launch_attn<AT_DEFAULT_EMU, false, QS, BND>(grid, st, tmQ, tmK, tmV, tmO, p);            \
-  } while (0)
-  if (q_norm != nullptr && variant != 6) {  // bounded softmax (experimental): any of the schedules of this file
-    if (variant == 7) MV_ATTN_EXP(1, true);
-    if (variant == 8) MV_ATTN_EXP(2, true);
-    MV_ATTN_EXP(0, true);
-  }
-  if (variant == 6) return launch_attn_v6(grid, st, tmQ, tmK, tmV, tmO, p, emu);
-  if (variant == 7) MV_ATTN_EXP(1, false);
-  if (variant == 8) MV_ATTN_EXP(2, false);
-#undef MV_ATTN_EXP
+  if (variant != 3) return launch_attn_pair(variant - 90, emu, trace != nullptr, B, Sq, H, st, tmQ, tmK, tmV, tmO, p);
+  dim3 grid((Sq + 255) / 256, H, B);
+  if (trace != nullptr) return launch_attn<4, true>(grid, st, tmQ, tmK, tmV, tmO, p);
   switch (emu) {
     case 0: return launch_attn<0, false>(grid, st, tmQ, tmK, tmV, tmO, p);
-    case 2: return launch_attn<2, false>(grid, st, tmQ, tmK, tmV, tmO, p);
-    case 4: return launch_attn<4, false>(grid, st, tmQ, tmK, tmV, tmO, p);
-    case 6: return launch_attn<6, false>(grid, st, tmQ, tmK, tmV, tmO, p);
     case 8: return launch_attn<8, false>(grid, st, tmQ, tmK, tmV, tmO, p);
-    default: MV_REQUIRE(false, "mova_b200_attn_fwd: MOVA_ATTN_EMU must be one of 0,2,4,6,8 (got %d)", emu);
+    default: return launch_attn<4, false>(grid, st, tmQ, tmK, tmV, tmO, p);
   }
-  return 0;
 }

@@ -1,4 +1,4 @@
-// Shared between the attention kernels (attn.cu: shipped v3 schedule, attn_v6.cu: experimental event-driven schedule).
+// Shared between the attention kernels (attn_pair.cu: the round-2 schedule, attn.cu: the round-1 schedule + C ABI).
 #pragma once
 
 #include "common.cuh"
@@ -12,9 +12,7 @@ struct AttnParams {
   float scale;       // softmax scale
   float scale_log2;  // scale * log2(e)
   float* lse;        // [B, H, Sq] or null
-  const float* qnorm;  // BOUNDED kernels: |q| per (b, query row, head), [B, Sq, H]
-  const float* kmax;   // BOUNDED kernels: max |k| per (b, head, 128-key block), [B, H, ceil(Skv/128)]
-  unsigned long long* trace;  // diagnostics (MOVA_ATTN_TRACE): 3 regions of 4096 (clock << 8 | event) records
+  unsigned long long* trace;  // diagnostics: 3 regions of 4096 (clock << 8 | event) records of CTA (0,0,0), or null
 };
 
 __device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
@@ -40,7 +38,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 }
 
 
-int launch_attn_v6(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
-                   const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p, int emu);
+int launch_attn_pair(int cg, int emu, bool trace, int B, int Sq, int H, cudaStream_t stream, const CUtensorMap& tmQ,
+                     const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p);
 
 }  // namespace mv

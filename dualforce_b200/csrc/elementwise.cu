@@ -258,68 +258,9 @@ __global__ void lse_merge_kernel(const __nv_bfloat16* __restrict__ o_parts, cons
   if (lse_out != nullptr && vh == 0) lse_out[static_cast<long long>(h) * rows + r] = m + __logf(denom);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Per-head L2 norms of a [B, S, H*128] view (q or k after RMSNorm + RoPE): row_norm[b, s, h] = |x[b, s, h, :]| and
-// block_max[b, h, s / 128] = max of it over a 128-row block -- the inputs of the bounded-softmax attention path.
-// One CTA per (128-row block, batch); a half-warp owns one head of one row (16 lanes x 16 bytes).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-head_norms_kernel(const __nv_bfloat16* __restrict__ x, long long bs, long long ss, int S, int H,
-                  float* __restrict__ row_norm, float* __restrict__ block_max) {
-  extern __shared__ int hmax[];  // H non-negative floats, compared as ints
-  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) hmax[i] = 0;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane >> 4, l16 = lane & 15;
-  for (int rr = warp; rr < 128; rr += 8) {
-    const int srow = blk * 128 + rr;
-    if (srow >= S) break;  // warp-uniform
-    const __nv_bfloat16* row = x + static_cast<long long>(b) * bs + static_cast<long long>(srow) * ss;
-    for (int h0 = 0; h0 < H; h0 += 2) {
-      const int h = h0 + half;
-      float ssq = 0.f;
-      if (h < H) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(row + static_cast<long long>(h) * 128 + l16 * 8), f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ssq = fmaf(f[e], f[e], ssq);
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);  // stays inside the half-warp
-      if (h < H && l16 == 0) {
-        const float n = sqrtf(ssq);
-        if (row_norm != nullptr) row_norm[(static_cast<long long>(b) * S + srow) * H + h] = n;
-        atomicMax(&hmax[h], __float_as_int(n));
-      }
-    }
-  }
-  __syncthreads();
-  if (block_max != nullptr)
-    for (int i = threadIdx.x; i < H; i += blockDim.x)
-      block_max[(static_cast<long long>(b) * H + i) * nblk + blk] = __int_as_float(hmax[i]);
-}
-
 }  // namespace mv
 
 extern "C" {
-
-int mova_b200_head_norms(const void* x, int64_t x_bs, int64_t x_ss, int B, int S, int H, int D, float* row_norm,
-                         float* block_max, void* stream) {
-  using namespace mv;
-  MV_REQUIRE(x != nullptr && (row_norm != nullptr || block_max != nullptr), "mova_b200_head_norms: null pointer");
-  MV_REQUIRE(D == 128, "mova_b200_head_norms: head_dim %d unsupported", D);
-  MV_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && H <= 8192 && S >= 0, "mova_b200_head_norms: bad shape B=%d S=%d H=%d", B, S, H);
-  MV_REQUIRE(x_ss % 8 == 0 && x_bs % 8 == 0 && x_ss >= static_cast<int64_t>(H) * D &&
-                 (reinterpret_cast<uintptr_t>(x) & 15) == 0,
-             "mova_b200_head_norms: rows must be 16-byte aligned");
-  if (S == 0) return 0;
-  dim3 grid((S + 127) / 128, B);
-  head_norms_kernel<<<grid, 256, H * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_bs, x_ss, S, H, row_norm, block_max);
-  MV_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
 
 int mova_b200_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int L, int d, float eps, const void* ln_w,
                         const void* ln_b, const float* shift, const float* scale, void* stream) {

@@ -1,7 +1,7 @@
 // Standalone device self-test of the C-ABI library (no torch): every kernel against a naive CUDA
 // reference on the same inputs.  One sub-command per process so a faulting kernel cannot poison the rest:
 //   selftest gemm <cta_group> <epilogue> <M> <N> <K> [iters]
-//   selftest attn <B> <Sq> <Skv> <H> [iters]
+//   selftest attn <B> <Sq> <Skv> <H> [iters] [variant 92|91|3] [emu 0|4|8] [trace file]
 //   selftest ln   <L> <d> <affine 0|1> <modulate 0|1>
 //   selftest rr   <L> <d> <rope_mode>
 //   selftest merge <parts> <rows> <H>
@@ -244,25 +244,16 @@ static int test_attn(int argc, char** argv) {
   CK(cudaMalloc(&oref, static_cast<size_t>(B) * Sq * row * 4));
   CK(cudaMalloc(&lseref, static_cast<size_t>(B) * H * Sq * 4));
   const float scale = 1.0f / sqrtf(128.f) * 3.0f;  // sharper than 1/sqrt(D) so the softmax is not flat
-  // MOVA_ATTN_BOUNDED=1: the bounded-softmax path (head norms + mova_b200_attn_fwd_ex), norms recomputed per call
-  const char* benv = getenv("MOVA_ATTN_BOUNDED");
-  const bool bounded = benv != nullptr && benv[0] == '1';
-  float *qn = nullptr, *km = nullptr;
-  if (bounded) {
-    CK(cudaMalloc(&qn, static_cast<size_t>(B) * Sq * H * 4));
-    CK(cudaMalloc(&km, static_cast<size_t>(B) * H * ((Skv + 127) / 128) * 4));
-    printf("  bounded softmax path\n");
-  }
+  const int variant = argc > 7 ? atoi(argv[7]) : 0;  // 0 = the shipped schedule (mova_b200_attn_fwd)
+  const int emu = argc > 8 ? atoi(argv[8]) : 4;
+  const char* trace_path = argc > 9 ? argv[9] : nullptr;
+  if (variant != 0) printf("  variant %d emu %d\n", variant, emu);
   auto run_attn = [&](float* lse_out) -> int {
-    if (!bounded)
+    if (variant == 0)
       return mova_b200_attn_fwd(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
                                 lse_out, B, Sq, Skv, H, D, scale, nullptr);
-    int rc = mova_b200_head_norms(q, q_bs, q_ss, B, Sq, H, D, qn, nullptr, nullptr);
-    if (rc != 0) return rc;
-    rc = mova_b200_head_norms(k, k_bs, k_ss, B, Skv, H, D, nullptr, km, nullptr);
-    if (rc != 0) return rc;
-    return mova_b200_attn_fwd_ex(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row, row,
-                                 lse_out, B, Sq, Skv, H, D, scale, qn, km, nullptr);
+    return mova_b200_attn_fwd_variant(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row,
+                                      row, lse_out, B, Sq, Skv, H, D, scale, variant, emu, nullptr, nullptr);
   };
   CKMV(run_attn(lse));
   CK(cudaDeviceSynchronize());
@@ -299,6 +290,24 @@ static int test_attn(int argc, char** argv) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= iters;
     printf("  timing: %.3f ms/iter  %.1f TFLOP/s\n", ms, 4.0 * B * H * Sq * Skv * D / ms * 1e-9);
+  }
+  if (trace_path != nullptr && variant != 0) {
+    // event timeline of CTA (0,0,0): 3 regions (softmax warpgroup A / B, issuer) of 4096 (clock << 8 | id) records
+    unsigned long long* tbuf;
+    const size_t tbytes = 3 * 4096 * sizeof(unsigned long long);
+    CK(cudaMalloc(&tbuf, tbytes));
+    CK(cudaMemset(tbuf, 0, tbytes));
+    CKMV(mova_b200_attn_fwd_variant(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, static_cast<long long>(Sq) * row,
+                                    row, nullptr, B, Sq, Skv, H, D, scale, variant, emu, tbuf, nullptr));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> host(3 * 4096);
+    CK(cudaMemcpy(host.data(), tbuf, tbytes, cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "wb");
+    if (f != nullptr) {
+      fwrite(host.data(), 1, tbytes, f);
+      fclose(f);
+      printf("  trace written to %s\n", trace_path);
+    }
   }
   return ok ? 0 : 1;
 }

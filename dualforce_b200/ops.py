@@ -5,7 +5,6 @@ is no fallback: a CPU tensor, a wrong dtype or a missing library raises.
 from __future__ import annotations
 
 import math
-import os
 from typing import Optional, Tuple
 
 import torch
@@ -15,7 +14,7 @@ from ._lib import EPI_BIAS, EPI_GELU_TANH, EPI_RESIDUAL, ROPE_HALF, ROPE_INTERLE
 
 __all__ = [
     "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32", "patchify", "unpatchify",
-    "sinusoidal_embedding", "gemv_f32", "cfg_euler_step", "head_norms",
+    "sinusoidal_embedding", "gemv_f32", "cfg_euler_step",
     "EPI_BIAS", "EPI_GELU_TANH", "EPI_RESIDUAL", "ROPE_NONE", "ROPE_INTERLEAVED", "ROPE_HALF",
 ]
 
@@ -127,40 +126,15 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
-# Experimental (off by default until it has run on hardware): skip the per-block row maximum of long attentions
-# whenever a Cauchy-Schwarz bound from per-head norms proves it unnecessary (csrc/attn.cu, BOUNDED).
-_BOUNDED_DEFAULT = os.environ.get("MOVA_ATTN_BOUNDED", "0") == "1"
-_BOUNDED_MIN_KEYS = 2048
-
-
-def head_norms(x: torch.Tensor, num_heads: int, *, rows: bool = False, blocks: bool = False):
-    """Per-head L2 norms of a flat ``[B, S, H*128]`` bf16 tensor (any row stride): ``row_norm [B, S, H]`` fp32 when
-    ``rows`` and / or ``block_max [B, H, ceil(S/128)]`` fp32 (max of the norm over blocks of 128 rows) when ``blocks``
-    -- the side inputs of the bounded-softmax attention path.  Returns ``(row_norm or None, block_max or None)``."""
-    _need(x, torch.bfloat16, "x")
-    if x.dim() != 3 or x.stride(2) != 1 or x.shape[2] != num_heads * 128:
-        raise _lib.MovaB200Error(f"head_norms: x must be [B, S, H*128] with a contiguous last dim, got {tuple(x.shape)}")
-    if not (rows or blocks):
-        raise _lib.MovaB200Error("head_norms: nothing requested")
-    B, S, _ = x.shape
-    rn = torch.empty(B, S, num_heads, dtype=torch.float32, device=x.device) if rows else None
-    bm = torch.empty(B, num_heads, (S + 127) // 128, dtype=torch.float32, device=x.device) if blocks else None
-    rc = _lib.load().mova_b200_head_norms(x.data_ptr(), x.stride(0) if B > 1 else x.stride(1) * S, x.stride(1), B, S,
-                                          num_heads, 128, rn.data_ptr() if rn is not None else None,
-                                          bm.data_ptr() if bm is not None else None, _stream())
-    _lib.check(rc, "mova_b200_head_norms")
-    return rn, bm
-
-
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, *, return_lse: bool = False,
               softmax_scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
-              bounded: Optional[bool] = None):
+              variant: Optional[int] = None, emu: int = 4):
     """``softmax(q k^T / sqrt(D)) v`` on the flat ``[B, S, H*D]`` layout of flash_attention()
     (wan_video_dit.py:58-91).  q/k/v may be column slices of a fused projection buffer (any row stride).
 
     Returns ``[B, Sq, H*D]`` bf16 (and ``lse [B, H, Sq]`` fp32, natural log, when ``return_lse``).
-    ``bounded`` (default: ``MOVA_ATTN_BOUNDED=1`` and at least 2048 keys) adds two small norm kernels and lets the
-    attention kernel skip row maxima it can prove unnecessary; the result is the same up to rounding.
+    ``variant`` (measurement only, see ``mova_b200_attn_fwd_variant``): 92 / 91 = round-2 schedule as a CTA pair /
+    single CTA, 3 = round-1 schedule; default: the library's shipped schedule.
     """
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _need(t, torch.bfloat16, n)
@@ -185,19 +159,13 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int,
     if rec is not None:  # bench.py: per-launch device time of the dominant kernel, on the launching stream
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    use_bound = bounded if bounded is not None else (_BOUNDED_DEFAULT and Skv >= _BOUNDED_MIN_KEYS)
-    if use_bound and D == 128:
-        qn, _ = head_norms(q, num_heads, rows=True)
-        _, km = head_norms(k, num_heads, blocks=True)
-        rc = _lib.load().mova_b200_attn_fwd_ex(
-            q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
+    args = (q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
             v.stride(1), out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr() if lse is not None else None, B,
-            Sq, Skv, num_heads, D, float(scale), qn.data_ptr(), km.data_ptr(), _stream())
+            Sq, Skv, num_heads, D, float(scale))
+    if variant is None:
+        rc = _lib.load().mova_b200_attn_fwd(*args, _stream())
     else:
-        rc = _lib.load().mova_b200_attn_fwd(
-            q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0),
-            v.stride(1), out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr() if lse is not None else None, B,
-            Sq, Skv, num_heads, D, float(scale), _stream())
+        rc = _lib.load().mova_b200_attn_fwd_variant(*args, int(variant), int(emu), None, _stream())
     _lib.check(rc, "mova_b200_attn_fwd")
     if rec is not None:
         e1 = torch.cuda.Event(enable_timing=True)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOVA_B200_ABI_VERSION 2
+#define MOVA_B200_ABI_VERSION 3
 
 /* epilogues of mova_b200_linear */
 #define MOVA_EPI_BIAS 0      /* C = A W^T + b                          nn.Linear                          */
@@ -88,24 +88,17 @@ int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, const void* k,
                        float* lse, int B, int Sq, int Skv, int H, int D, float softmax_scale, void* stream);
 
 /*
- * Same attention with the bounded-softmax shortcut (experimental): q_norm[b, s, h] = |q[b, s, h, :]| (fp32
- * [B, Sq, H]) and k_block_max[b, h, j] = max over keys 128j..128j+127 of |k[b, s, h, :]| (fp32 [B, H, ceil(Skv/128)]),
- * both from mova_b200_head_norms.  While |q||k_max| * scale stays within 2^64 of the running reference point the
- * kernel skips the row-max reduction; otherwise it takes the exact path, so the result equals mova_b200_attn_fwd's
- * up to fp rounding for any input.  Both pointers NULL == mova_b200_attn_fwd.
+ * Development / measurement entry: the same attention with the schedule chosen explicitly.
+ *   variant 92: round-2 schedule, CTA pair (cta_group::2)  -- what mova_b200_attn_fwd runs
+ *   variant 91: round-2 schedule, single CTA per 128-row query tile
+ *   variant  3: round-1 schedule (two query tiles per CTA, S/P aliased)
+ *   emu: share of the exponentials evaluated as a polynomial on the FMA pipe, in 16ths of the score pairs (0, 4, 8)
+ *   trace: NULL, or device memory for 3 x 4096 u64 event records (clock << 8 | id) of CTA (0,0,0)
  */
-int mova_b200_attn_fwd_ex(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs, int64_t k_ss,
-                          const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs, int64_t o_ss, float* lse,
-                          int B, int Sq, int Skv, int H, int D, float softmax_scale, const float* q_norm,
-                          const float* k_block_max, void* stream);
-
-/*
- * Per-head L2 norms of a [B, S, H, 128] bf16 view (element (b,s,h,d) at x + b*x_bs + s*x_ss + h*128 + d):
- *   row_norm  fp32 [B, S, H]              or NULL
- *   block_max fp32 [B, H, ceil(S/128)]    or NULL   (max of the norm over each block of 128 rows)
- */
-int mova_b200_head_norms(const void* x, int64_t x_bs, int64_t x_ss, int B, int S, int H, int D, float* row_norm,
-                         float* block_max, void* stream);
+int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs, int64_t k_ss,
+                               const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs, int64_t o_ss,
+                               float* lse, int B, int Sq, int Skv, int H, int D, float softmax_scale, int variant,
+                               int emu, unsigned long long* trace, void* stream);
 
 /*
  * Merge `n_parts` partial attention results over disjoint key sets (split-KV / context-parallel v2a):

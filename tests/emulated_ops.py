@@ -80,21 +80,7 @@ def linear(x, weight, bias=None, *, epilogue=EPI_BIAS, residual=None, gate=None,
     return out
 
 
-def head_norms(x, num_heads, *, rows=False, blocks=False):
-    _count("head_norms")
-    _need(x, BF16, "x")
-    B, S, HD = x.shape
-    n = x.float().reshape(B, S, num_heads, 128).norm(dim=-1)  # [B, S, H]
-    bm = None
-    if blocks:
-        nb = (S + 127) // 128
-        pad = torch.zeros(B, nb * 128, num_heads)
-        pad[:, :S] = n
-        bm = pad.reshape(B, nb, 128, num_heads).amax(dim=2).permute(0, 2, 1).contiguous()
-    return (n.contiguous() if rows else None), bm
-
-
-def attention(q, k, v, num_heads, *, return_lse=False, softmax_scale=None, out=None, bounded=None):
+def attention(q, k, v, num_heads, *, return_lse=False, softmax_scale=None, out=None, variant=None, emu=4):
     _count("attention")
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _need(t, BF16, n)
@@ -302,7 +288,7 @@ def cfg_euler_step(posi, nega, sample, cfg_scale, dsigma, *, out=None):
     return res
 
 
-ENTRY_POINTS = dict(linear=linear, attention=attention, head_norms=head_norms, layernorm=layernorm, rmsnorm_rope_=rmsnorm_rope_,
+ENTRY_POINTS = dict(linear=linear, attention=attention, layernorm=layernorm, rmsnorm_rope_=rmsnorm_rope_,
                     lse_merge=lse_merge, add_to_f32=add_to_f32, patchify=patchify, unpatchify=unpatchify,
                     sinusoidal_embedding=sinusoidal_embedding, gemv_f32=gemv_f32,
                     cfg_euler_step=cfg_euler_step)

@@ -68,14 +68,13 @@ def test_every_ops_entry_point_rejects_cpu_tensors():
         lambda: B.ops.sinusoidal_embedding(256, torch.zeros(1)),
         lambda: B.ops.gemv_f32(f32, bf),
         lambda: B.ops.cfg_euler_step(bf, None, torch.zeros(8, 128), 1.0, -0.1),
-        lambda: B.ops.head_norms(bf[None], 1, rows=True),
     ]
     for i, call in enumerate(calls):
         with pytest.raises(B.MovaB200Error):
             call()
     assert {n for n in B.ops.__all__ if not n.startswith(("EPI_", "ROPE_"))} >= {
         "linear", "attention", "layernorm", "rmsnorm_rope_", "lse_merge", "add_to_f32", "patchify", "unpatchify",
-        "sinusoidal_embedding", "gemv_f32", "cfg_euler_step", "head_norms"}
+        "sinusoidal_embedding", "gemv_f32", "cfg_euler_step"}
 
 
 def test_ctypes_signatures_match_the_header_argument_by_argument():

@@ -247,43 +247,38 @@ def test_swap_modules_on_reference_pipeline_runs_the_reference_loop_shape(emu, s
 
 
 def test_bench_model_builder_composes_with_the_step(emu):
-    """bench.py builds the block lists exactly as the forward-level measurement always has and grafts them onto
-    zero-layer tower twins for the step-level e2e: the composition must run the step (host logic only here)."""
+    """bench.py's model builder (tower twins with both video experts, bridge, bound drop-in methods) runs the step and
+    the fused CFG + Euler update the timed region is made of (host logic only here; tests/dryrun_bench.py runs the
+    whole arm)."""
     import bench
+    from dualforce_b200 import step
 
     cfg = dict(O.TINY_CFG, grid_size=(2, 2, 3), audio_len=9)
-    pipe = bench.build_model(cfg, torch.device("cpu"), with_step=True)
+    pipe = bench.build_model(cfg, torch.device("cpu"), experts=2)
     assert len(pipe.video_dit.blocks) == cfg["visual_layers"] and len(pipe.audio_dit.blocks) == cfg["audio_layers"]
+    assert pipe.video_dit_2 is not None and pipe.video_dit_2 is not pipe.video_dit
     assert pipe.video_dit.patch_embedding.weight.dtype == torch.bfloat16
     S = bench.STEP_360P
-    g = torch.Generator().manual_seed(0)
-    lat = torch.randn(1, S["visual_in_dim"], 2, 4, 6, generator=g)
-    alat = torch.randn(1, S["audio_in_dim"], 9, generator=g)
-    ctx = torch.randn(1, cfg["text_len"], S["text_dim"], generator=g).to(torch.bfloat16)
-    v, a = pipe.inference_single_step(visual_dit=pipe.video_dit, visual_latents=lat, audio_latents=alat, context=ctx,
-                                      timestep=torch.tensor([900.0]), audio_timestep=None, video_fps=24.0)
-    assert v.shape == (1, S["visual_out_dim"], 2, 4, 6) and a.shape == (1, S["audio_out_dim"], 9)
-    assert torch.isfinite(v.float()).all() and torch.isfinite(a.float()).all()
-    # the bench's step-level e2e leg itself (host logic: buffers, memo warm-up, launch accounting, JSON object)
-    import time
-
-    def timed(fn, steps):
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-        return (time.perf_counter() - t0) * 1e3
-
-    e2e = bench.measure_step_api(pipe, cfg, torch.device("cpu"), None, 0, 2, timed, lambda: sum(emu.values()), pin=False)
-    assert e2e["value"] > 0 and e2e["unit"] == "steps/s" and e2e["ms_per_step"] > 0
-    assert e2e["h2d_bytes_per_step"] == (36 * 2 * 4 * 6 + S["audio_in_dim"] * 9 + 1) * 4
-    assert e2e["d2h_bytes_per_step"] == 2 * (16 * 2 * 4 * 6 + S["audio_out_dim"] * 9) * 2
+    host = bench.host_step_inputs(cfg, pin=False)
+    assert host["latents"].shape == (1, 16, 2, 4, 6) and host["condition"].shape == (1, 20, 2, 4, 6)
+    x_in = torch.cat([host["latents"], host["condition"]], dim=1)
+    kw = dict(visual_dit=pipe.video_dit, visual_latents=x_in, audio_latents=host["audio_latents"],
+              timestep=torch.tensor([900.0]), audio_timestep=None, video_fps=24.0)
+    before = sum(emu.values())
+    pv, pa = pipe.inference_single_step(context=host["context_pos"], **kw)
+    per_forward_first = sum(emu.values()) - before
+    nv, na = pipe.inference_single_step(context=host["context_neg"], **kw)
+    assert pv.shape == (1, S["visual_out_dim"], 2, 4, 6) and pa.shape == (1, S["audio_out_dim"], 9)
+    assert torch.isfinite(pv.float()).all() and torch.isfinite(pa.float()).all()
+    ts, sig = bench.flow_match_schedule(50)
+    assert abs(float(ts[0]) - 1000.0) < 1e-3 and float(sig[-1]) > 0 and all(sig[i] > sig[i + 1] for i in range(49))
+    lat_next = step.guided_update(pv, nv, host["latents"], 5.0, float(sig[0]), float(sig[1]))
+    want = host["latents"] + (nv.float() + 5.0 * (pv.float() - nv.float())) * (float(sig[1]) - float(sig[0]))
+    assert torch.allclose(lat_next, want, rtol=1e-5, atol=1e-5)
     n_blocks = cfg["visual_layers"] + cfg["audio_layers"]
-    per_forward = 17 * n_blocks + 14 * min(cfg["visual_layers"], cfg["audio_layers"]) - 2 * n_blocks  # text k/v memoised
-    # + per forward: 2 patchify + 2 patch GEMMs + 2 x (add, LN, GEMM, unpatchify) heads; per step: 2 x 4 time kernels
-    assert e2e["gpu_launches_per_step"] == 2 * (per_forward + 4 + 8) + 8, e2e
-    # the forward-level builder is unchanged
-    bare = bench.build_model(cfg, torch.device("cpu"), with_step=False)
-    assert not hasattr(bare.video_dit, "patch_embedding") and not hasattr(bare, "inference_single_step")
+    # 17 launches per block + 14 per bridge layer; per forward: 2 patchify + 2 patch GEMMs + 2 x (add, LN, GEMM,
+    # unpatchify) heads; first forward of a step: 8 time-embedding kernels + 4 text-embedding GEMMs
+    assert per_forward_first == 17 * n_blocks + 14 * min(cfg["visual_layers"], cfg["audio_layers"]) + 4 + 8 + 8 + 4
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
@@ -380,25 +375,27 @@ def test_end_of_schedule_latents_host_logic(emu, step_case):
     assert emu["linear"] + emu["layernorm"] + emu["rmsnorm_rope_"] + emu["attention"] + emu["add_to_f32"] < 8 * (per_forward + 12)
 
 
-def test_split_kv_bridge_attention_host_logic(emu, monkeypatch):
-    """MOVA_V2A_SPLITS: keys cut in equal chunks run as the batch dimension of one launch + exact LSE merge."""
+def test_split_kv_bridge_attention_host_logic(emu):
+    """Few queries against many keys: the keys are cut in equal chunks run as the batch dimension of one launch, then
+    merged exactly with their log-sum-exps (modules._kv_splits picks the factor from the shape alone)."""
     import dualforce_b200 as B
+    from dualforce_b200.modules import _kv_splits
 
-    monkeypatch.setenv("MOVA_V2A_SPLITS", "5")
+    assert _kv_splits(403, 43120, 12) > 1 and 43120 % _kv_splits(403, 43120, 12) == 0  # the v2a bridge shape
+    assert _kv_splits(43120, 403, 40) == 1 and _kv_splits(403, 4400, 12) == 1 and _kv_splits(403, 8209, 12) == 1
     g = torch.Generator().manual_seed(2)
     dim, kv_dim, H = 256, 384, 2
     cca = B.ConditionalCrossAttention(dim, kv_dim, H).to(torch.bfloat16)
     for prm in cca.parameters():
         prm.data = (torch.randn(prm.shape, generator=g) * (0.05 if prm.dim() > 1 else 0.1)).to(torch.bfloat16)
     x = torch.randn(1, 7, dim, generator=g).to(torch.bfloat16)
-    y = torch.randn(1, 8200 - 8200 % 5, kv_dim, generator=g).to(torch.bfloat16)  # 8200 keys: 5 chunks of 1640
+    y = torch.randn(1, 8192, kv_dim, generator=g).to(torch.bfloat16)
+    n = _kv_splits(7, 8192, H)
+    assert n > 1
     split = cca(x, y)
     assert emu["lse_merge"] == 1 and emu["attention"] == 1
-    monkeypatch.setenv("MOVA_V2A_SPLITS", "1")
-    plain = cca(x, y)
+    q = cca.project_q(x, None)
+    k, v = cca.project_kv(y, None)
+    plain = B.ops.linear(cca.attn(q, k, v), cca.o.weight, cca.o.bias)
     assert emu["lse_merge"] == 1 and emu["attention"] == 2
     assert_close(split, plain.float(), "split-KV vs unsplit", ratio=1e-2, fro=6e-3)
-    # not applicable (many queries, or keys not divisible): falls back silently
-    monkeypatch.setenv("MOVA_V2A_SPLITS", "7")
-    cca(x, y)
-    assert emu["lse_merge"] == 1
