@@ -35,6 +35,17 @@ def reference_attention(q, k, v, num_heads):
         return o.transpose(1, 2).reshape(B, Sq, HD), "sdpa"
 
 
+def sdpa_cudnn(q, k, v, num_heads):
+    """torch SDPA with the cuDNN fused-attention back end forced (the fastest library attention on this box,
+    profiles/r02_kernels_vs_libs*.jsonl) -- the bar beside the reference's own choice."""
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    B, Sq, HD = q.shape
+    qh, kh, vh = (t.view(B, -1, num_heads, HD // num_heads).transpose(1, 2) for t in (q, k, v))
+    with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+        return torch.nn.functional.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, Sq, HD)
+
+
 def time_fn(fn, iters, flush):
     for _ in range(3):
         fn()
@@ -70,14 +81,20 @@ def main():
                 q = torch.randn(1, sq, heads * 128, device="cuda", generator=g).to(torch.bfloat16)
                 k = torch.randn(1, skv, heads * 128, device="cuda", generator=g).to(torch.bfloat16)
                 v = torch.randn(1, skv, heads * 128, device="cuda", generator=g).to(torch.bfloat16)
-                ours = B.ops.attention(q, k, v, heads)
+                attn = B.AttentionModule(heads)  # the product's attention processor (splits the keys for v2a)
+                ours = attn(q, k, v)
                 ref, backend = reference_attention(q, k, v, heads)
                 err = (ours.float() - ref.float()).abs().max().item() / max(ref.float().abs().max().item(), 1e-30)
-                t_ours = time_fn(lambda: B.ops.attention(q, k, v, heads), args.iters, flush)
+                t_ours = time_fn(lambda: attn(q, k, v), args.iters, flush)
                 t_ref = time_fn(lambda: reference_attention(q, k, v, heads), args.iters, flush)
                 flops = 4.0 * heads * sq * skv * 128
+                try:
+                    t_cudnn = time_fn(lambda: sdpa_cudnn(q, k, v, heads), args.iters, flush)
+                except Exception:  # noqa: BLE001 -- back end unavailable for this shape
+                    t_cudnn = None
                 print(json.dumps({"case": name, "L_v": lv, "L_a": la, "heads": heads, "ms": t_ours, "ref_ms": t_ref,
-                                  "ref_backend": backend, "speedup": t_ref / t_ours,
+                                  "ref_backend": backend, "speedup": t_ref / t_ours, "sdpa_cudnn_ms": t_cudnn,
+                                  "speedup_vs_sdpa_cudnn": (t_cudnn / t_ours) if t_cudnn else None,
                                   "tflops": flops / t_ours * 1e-9, "ref_tflops": flops / t_ref * 1e-9,
                                   "max_err_ratio": err, "parity_ok": bool(err < 2e-2 and math.isfinite(err))}),
                       flush=True)

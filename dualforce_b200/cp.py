@@ -94,6 +94,22 @@ class UlyssesPlan:
         return torch.cat(idx)
 
 
+def head_group_sets(heads_per_rank: int, want: int = 2):
+    """(number of head groups, attention sets) for the pipelined Ulysses exchange of ``heads_per_rank`` heads.
+
+    The exchange buffers are laid out in equal head groups (a constraint of the segmented GEMM operands).  When the
+    heads split evenly in ``want`` groups, every group is one exchange and one attention launch (20 heads -> 2 x 10,
+    10 -> 2 x 5: the round-1 configuration).  An odd count (cp = 8: 5 heads per rank) is exchanged head by head and
+    attended in two sets of consecutive groups -- ``[[0, 1, 2], [3, 4]]`` -- each set being one attention launch with
+    the groups as its batch dimension, so the second set travels while the first is in the tensor cores and the
+    first set's outputs return while the second is attended."""
+    g = UlyssesPlan.pick_groups(heads_per_rank, want)
+    if g >= min(want, heads_per_rank) or heads_per_rank < 3:
+        return g, [[i] for i in range(g)]
+    first = (heads_per_rank + 1) // 2
+    return heads_per_rank, [list(range(0, first)), list(range(first, heads_per_rank))]
+
+
 def all_to_all_rows(inp: torch.Tensor, in_rows: Sequence[int], out_rows: Sequence[int],
                     group: Optional[dist.ProcessGroup], out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """all_to_all_single over dim 0 of a ``[sum(in_rows), C]`` matrix: rows ``in_rows[r]`` go to rank r, the result

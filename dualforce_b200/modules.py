@@ -132,7 +132,23 @@ class AttentionModule(nn.Module):
         self.num_heads = num_heads
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+        splits = _kv_splits(q.shape[1], k.shape[1], self.num_heads) if q.shape[0] == 1 else 1
+        if splits > 1:
+            return split_kv_attention(q, k, v, self.num_heads, splits)
         return ops.attention(q, k, v, self.num_heads)
+
+
+def split_kv_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads: int, splits: int) -> torch.Tensor:
+    """Few queries, many keys (v2a: 403 audio queries x 43 120 video keys x 12 heads = 48 CTAs on 148 SMs): cut the
+    keys in ``splits`` equal chunks, run them as the BATCH dimension of one attention launch (48 x splits CTAs) and
+    merge the partial results exactly with their log-sum-exps."""
+    _, Sq, HD = q.shape
+    chunk = k.shape[1] // splits
+    kc = k[0].unflatten(0, (splits, chunk))  # strided view [splits, chunk, HD] of the fused k|v buffer
+    vc = v[0].unflatten(0, (splits, chunk))
+    qe = q.expand(splits, Sq, HD).contiguous()  # the kernel's tensor map wants a real batch stride (6 MB at 360p)
+    o, lse = ops.attention(qe, kc, vc, num_heads, return_lse=True)
+    return ops.lse_merge(o, lse, num_heads).unsqueeze(0)
 
 
 class USPAttention(nn.Module):
@@ -440,22 +456,7 @@ class ConditionalCrossAttention(nn.Module):
     def attend(self, x, y, x_freqs=None, y_freqs=None):
         q = self.project_q(x, x_freqs)
         k, v = self.project_kv(y, y_freqs)
-        splits = _kv_splits(q.shape[1], k.shape[1], self.num_heads) if q.shape[0] == 1 else 1
-        if splits > 1:
-            return self._attend_split_kv(q, k, v, splits)
-        return self.attn(q, k, v)
-
-    def _attend_split_kv(self, q, k, v, splits: int):
-        """Few queries, many keys (v2a: 403 audio queries x 43 120 video keys x 12 heads = 24 CTAs on 148 SMs): cut the
-        keys in ``splits`` equal chunks, run them as the BATCH dimension of one attention launch (24 x splits CTAs, all
-        resident at once), and merge the partial results exactly with their log-sum-exps."""
-        _, Sq, HD = q.shape
-        chunk = k.shape[1] // splits
-        kc = k[0].unflatten(0, (splits, chunk))  # strided view [splits, chunk, HD] of the fused k|v buffer
-        vc = v[0].unflatten(0, (splits, chunk))
-        qe = q.expand(splits, Sq, HD).contiguous()  # the kernel's tensor map wants a real batch stride (6 MB at 360p)
-        o, lse = ops.attention(qe, kc, vc, self.num_heads, return_lse=True)
-        return ops.lse_merge(o, lse, self.num_heads).unsqueeze(0)
+        return self.attn(q, k, v)  # AttentionModule: splits the keys when the launch would not fill the GPU
 
     def forward(self, x: torch.Tensor, y: torch.Tensor, x_freqs=None, y_freqs=None) -> torch.Tensor:
         return ops.linear(self.attend(x, y, x_freqs, y_freqs), self.o.weight, self.o.bias)

@@ -30,17 +30,15 @@ __all__ = ["forward_dual_tower_dit", "install", "swap_modules", "CPRuntime", "Gr
 class CPRuntime:
     """Process-group handle + the communication stream the all-to-alls are queued on."""
 
-    def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: Optional[int] = None,
-                 attn_streams: Optional[int] = None):
+    def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: Optional[int] = None):
         self.group, self.rank, self.size, self.device = group, rank, size, device
-        # Tuning knobs (defaults = the measured round-1 configuration: 2 head groups, attention on the main stream).
-        # MOVA_CP_HEAD_GROUPS=5 with MOVA_CP_ATTN_STREAMS=2 is the experiment for cp = 8, where 5 heads per rank do not
-        # split in two and the all-to-alls are fully exposed: one head per group, and the per-group attention kernels
-        # spread over side streams so that their partial last waves overlap instead of serialising (unmeasured).
-        self.head_groups = int(os.environ.get("MOVA_CP_HEAD_GROUPS", "2")) if head_groups is None else head_groups
-        n_attn = int(os.environ.get("MOVA_CP_ATTN_STREAMS", "0")) if attn_streams is None else attn_streams
-        self.comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
-        self.attn_streams = [torch.cuda.Stream(device=device) for _ in range(n_attn)] if device.type == "cuda" else []
+        # head groups the Ulysses exchange is pipelined in when the heads per rank split evenly (2: measured in round 1
+        # at cp = 2 / 4); an odd count (5 heads per rank at cp = 8) is exchanged head by head and attended in two sets
+        self.head_groups = 2 if head_groups is None else head_groups
+        cuda = device.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=device) if cuda else None
+        # the replicated audio tower and the v2a bridge direction run here, beside the video block of the same layer
+        self.audio_stream = torch.cuda.Stream(device=device) if cuda else None
 
     @classmethod
     def from_mesh(cls, cp_mesh, device: torch.device, head_groups: Optional[int] = None) -> "CPRuntime":
@@ -89,8 +87,8 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
     RMSNorm + RoPE on the segmented buffer, per head group {all-to-all, attention, all-to-all back} with the
     exchanges on the communication stream, o-projection reading source-rank-major with the gated residual fused."""
     sa = block.self_attn
-    plan = cpmod.UlyssesPlan(sa.num_heads, sa.head_dim, rt.size,
-                             cpmod.UlyssesPlan.pick_groups(sa.num_heads // rt.size, rt.head_groups))
+    groups, sets = cpmod.head_group_sets(sa.num_heads // rt.size, rt.head_groups)
+    plan = cpmod.UlyssesPlan(sa.num_heads, sa.head_dim, rt.size, groups)
     w, b, nq, nk, wo = _cp_weights(block, plan)
     Lc = h.shape[1]
     G, cp, wd = plan.groups, plan.cp, plan.w
@@ -122,34 +120,27 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
     ready = record(main)
     # every buffer is allocated on the compute stream; the side stream only fills it between two events
     L = sum(rows_per_rank)
-    recv = [torch.empty(L, 3 * wd, dtype=torch.bfloat16, device=h.device) for _ in range(G)]
+    recv = torch.empty(G, L, 3 * wd, dtype=torch.bfloat16, device=h.device)
     back = torch.empty(G, cp, Lc, wd, dtype=torch.bfloat16, device=h.device)
+    outs = [torch.empty(len(gs), L, wd, dtype=torch.bfloat16, device=h.device) for gs in sets]
     in_done = []
     with on_comm():
         wait(comm, ready)
         for g in range(G):
             cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
             in_done.append(record(comm))
-    outs, out_done = [], []
-    side = rt.attn_streams if comm is not None else []
-    if side:  # attention outputs allocated up front on the compute stream, like recv / back
-        outs = [torch.empty(1, L, wd, dtype=torch.bfloat16, device=h.device) for _ in range(G)]
-    for g in range(G):
-        qkv = recv[g].unsqueeze(0)
-        if side:
-            st = side[g % len(side)]
-            with torch.cuda.stream(st):
-                wait(st, in_done[g])
-                o = ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=outs[g])
-                att = record(st)
-        else:
-            wait(main, in_done[g])
-            o = ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg)  # [1, L, wd]
-            outs.append(o)
-            att = record(main)
+    out_done = []
+    for gs, o in zip(sets, outs):
+        # one attention launch per SET of consecutive head groups: the groups are its batch dimension (stride L*3*wd),
+        # so a set starts as soon as its last group has landed while the next set is still on the wire
+        wait(main, in_done[gs[-1]])
+        qkv = recv[gs[0]:gs[-1] + 1]
+        ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=o)
+        att = record(main)
         with on_comm():
             wait(comm, att)
-            cpmod.gather_heads(o[0], rows_per_rank, rt.rank, rt.group, out=back[g])
+            for i, g in enumerate(gs):
+                cpmod.gather_heads(o[i], rows_per_rank, rt.rank, rt.group, out=back[g])
             out_done.append(record(comm))
     for ev in out_done:
         wait(main, ev)
@@ -254,17 +245,53 @@ def _forward_eager(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tens
     x_loc = visual_x[:, s0:s1].contiguous()
     v_tab_loc = (v_tab[0][s0:s1].contiguous(), v_tab[1][s0:s1].contiguous())
     v_cs_loc = (v_cs[0][s0:s1].contiguous(), v_cs[1][s0:s1].contiguous()) if v_cs is not None else None
+    # Two streams per layer.  The video side (a2v bridge direction + video block, with its all-to-alls) stays on the
+    # current stream; the replicated audio side (v2a bridge direction with its small all-gathers + audio block: ~35
+    # launch-bound kernels on 403 tokens that do not shrink with cp) runs on rt.audio_stream beside it.  Both bridge
+    # directions read the PRE-bridge states of the other tower, so each layer starts with one event exchange.
+    aud = rt.audio_stream
+    main = torch.cuda.current_stream() if aud is not None else None
+
+    def on_audio():
+        return torch.cuda.stream(aud) if aud is not None else contextlib.nullcontext()
+
+    def record(stream):
+        if aud is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def wait(stream, ev):
+        if ev is not None:
+            stream.wait_event(ev)
+
+    if aud is not None:
+        aud.wait_stream(main)
+    ev_a = None  # audio_x of this layer is complete on the audio stream
     for i in range(min_layers):
-        if bridge.should_interact(i, "a2v"):
+        ev_v = record(main)  # x_loc of this layer is complete on the main stream
+        wait(main, ev_a)
+        x_pre, a_pre = x_loc, audio_x
+        if aud is not None:  # tensors read on a stream other than the one that allocated them
+            a_pre.record_stream(main)
+            x_pre.record_stream(aud)
+        a2v = bridge.should_interact(i, "a2v")
+        if a2v:
             # a2v: local video queries x replicated audio keys -- no communication
-            new_v = bridge.audio_to_video_conditioners[str(i)].forward_residual(
-                x_loc, audio_x, v_cs_loc, a_cs, scale_for(a2v_condition_scale))
-            if bridge.should_interact(i, "v2a"):
-                audio_x = _v2a_cp(bridge.video_to_audio_conditioners[str(i)], audio_x, x_loc, a_cs, v_cs_loc,
+            x_loc = bridge.audio_to_video_conditioners[str(i)].forward_residual(
+                x_pre, a_pre, v_cs_loc, a_cs, scale_for(a2v_condition_scale))
+        with on_audio():
+            wait(aud, ev_v)
+            if a2v and bridge.should_interact(i, "v2a"):
+                audio_x = _v2a_cp(bridge.video_to_audio_conditioners[str(i)], a_pre, x_pre, a_cs, v_cs_loc,
                                   scale_for(v2a_condition_scale), rt)
-            x_loc = new_v
+            audio_x = audio_dit.blocks[i](audio_x, audio_context, audio_t_mod, a_tab)  # replicated
+            ev_a = record(aud)
         x_loc = _video_block_cp(visual_dit.blocks[i], x_loc, visual_context, visual_t_mod, v_tab_loc, rt, rows)
-        audio_x = audio_dit.blocks[i](audio_x, audio_context, audio_t_mod, a_tab)  # replicated
+    wait(main, ev_a)
+    if aud is not None:
+        audio_x.record_stream(main)
     for i in range(min_layers, visual_layers):
         x_loc = _video_block_cp(visual_dit.blocks[i], x_loc, visual_context, visual_t_mod, v_tab_loc, rt, rows)
     if not _gather:

@@ -97,9 +97,10 @@ def _worker(rank, world, port, grid, heads, results):
         dist.destroy_process_group()
 
 
-# 60 tokens -> 30 + 30; 9 tokens -> 5 + 4 (ragged); 4 ranks: 18 tokens -> 5 + 5 + 5 + 3, one video head per rank
+# 60 tokens -> 30 + 30; 9 tokens -> 5 + 4 (ragged); 4 ranks: 18 tokens -> 5 + 5 + 5 + 3, one video head per rank;
+# 6 heads on 2 ranks: an odd head count per rank (like 5 at cp = 8): exchanged head by head, attended as sets [[0, 1], [2]]
 @pytest.mark.parametrize("world,grid,heads", [(2, (3, 4, 5), None), (2, (1, 3, 3), None), (2, (2, 3, 3), 4),
-                                              (4, (2, 3, 3), 4)])
+                                              (4, (2, 3, 3), 4), (2, (2, 3, 3), 6)])
 def test_step_context_parallel_gloo(world, grid, heads):
     mgr = mp.Manager()
     results = mgr.dict()

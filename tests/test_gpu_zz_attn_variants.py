@@ -97,6 +97,10 @@ def test_split_kv_bridge_attention_on_device():
     y = torch.randn(1, 43120, 5120, generator=g).to(torch.bfloat16).cuda()
     q = cca.project_q(x, None)
     k, v = cca.project_kv(y, None)
-    plain = cca.attn(q, k, v)
-    split = cca._attend_split_kv(q, k, v, 5)
+    from dualforce_b200.modules import split_kv_attention
+
+    plain = B.ops.attention(q, k, v, 12)
+    split = split_kv_attention(q, k, v, 12, 5)
+    auto = cca.attn(q, k, v)  # the attention processor picks the split factor from the shape
+    assert_close(auto, plain.float().cpu(), "auto split-KV vs unsplit", ratio=1e-2, fro=6e-3)
     assert_close(split, plain.float().cpu(), "split-KV vs unsplit", ratio=1e-2, fro=6e-3)

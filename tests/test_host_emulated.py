@@ -396,6 +396,6 @@ def test_split_kv_bridge_attention_host_logic(emu):
     assert emu["lse_merge"] == 1 and emu["attention"] == 1
     q = cca.project_q(x, None)
     k, v = cca.project_kv(y, None)
-    plain = B.ops.linear(cca.attn(q, k, v), cca.o.weight, cca.o.bias)
+    plain = B.ops.linear(B.ops.attention(q, k, v, H), cca.o.weight, cca.o.bias)
     assert emu["lse_merge"] == 1 and emu["attention"] == 2
     assert_close(split, plain.float(), "split-KV vs unsplit", ratio=1e-2, fro=6e-3)
