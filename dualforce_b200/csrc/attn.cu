@@ -403,6 +403,9 @@ static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, c
 #ifndef MOVA_ATTN_DEFAULT_VARIANT
 #define MOVA_ATTN_DEFAULT_VARIANT 92
 #endif
+#ifndef MOVA_ATTN_SHORT_KV_BLOCKS
+#define MOVA_ATTN_SHORT_KV_BLOCKS 8
+#endif
 #ifndef MOVA_ATTN_DEFAULT_EMU
 #define MOVA_ATTN_DEFAULT_EMU 4
 #endif
@@ -411,8 +414,15 @@ extern "C" int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, con
                                   const void* v, int64_t v_bs, int64_t v_ss, void* o, int64_t o_bs, int64_t o_ss,
                                   float* lse, int B, int Sq, int Skv, int H, int D, float softmax_scale,
                                   void* stream) {
+  // Schedule by shape (measured on B200, profiles/r02_attn_schedules.log):
+  //  * long key sequences (video self-attention, v2a bridge): the round-2 CTA-pair kernel -- 1325 vs 1273 TFLOP/s at
+  //    43120 x 43120 x 40 heads, and twice the CTAs for the 403-query v2a shape (445 vs 211 TFLOP/s);
+  //  * a handful of key blocks against many queries (text cross-attention: 512 keys, a2v bridge: 403 keys): the per-CTA
+  //    prologue / epilogue dominates, and the round-1 kernel amortises it over 256 query rows per CTA (920 vs 613).
+  const int n_kv = (Skv + 127) / 128;
+  const int variant = (n_kv <= MOVA_ATTN_SHORT_KV_BLOCKS && Sq > 256) ? 3 : MOVA_ATTN_DEFAULT_VARIANT;
   return mova_b200_attn_fwd_variant(q, q_bs, q_ss, k, k_bs, k_ss, v, v_bs, v_ss, o, o_bs, o_ss, lse, B, Sq, Skv, H, D,
-                                    softmax_scale, MOVA_ATTN_DEFAULT_VARIANT, MOVA_ATTN_DEFAULT_EMU, nullptr, stream);
+                                    softmax_scale, variant, MOVA_ATTN_DEFAULT_EMU, nullptr, stream);
 }
 
 extern "C" int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs,
@@ -429,7 +439,7 @@ extern "C" int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q
   MV_REQUIRE(softmax_scale > 0.f, "mova_b200_attn_fwd: softmax_scale must be positive");
   MV_REQUIRE(variant == 3 || variant == 91 || variant == 92, "mova_b200_attn_fwd_variant: variant must be 3 (round-1 "
              "schedule), 91 (round-2 schedule, single CTA) or 92 (round-2 schedule, CTA pair); got %d", variant);
-  MV_REQUIRE(emu == 0 || emu == 4 || emu == 8, "mova_b200_attn_fwd_variant: emu must be 0, 4 or 8 (got %d)", emu);
+  MV_REQUIRE(emu == 0 || emu == 4 || emu == 6 || emu == 8, "mova_b200_attn_fwd_variant: emu must be 0, 4, 6 or 8 (got %d)", emu);
   const int64_t row = static_cast<int64_t>(H) * D;
   MV_REQUIRE(q_ss >= row && k_ss >= row && v_ss >= row && o_ss >= row,
              "mova_b200_attn_fwd: sequence stride smaller than H*D");

@@ -175,6 +175,17 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t s[128];
 #pragma unroll
       for (int q = 0; q < 4; ++q) tmem_ld_x32(t_s + q * 32, reinterpret_cast<uint32_t(&)[32]>(s[q * 32]));
+      // while the score tile is on its way from tensor memory: take the reference maximum published by the owner of
+      // block j-1 (the other warpgroup, which passed this point most of a block ago)
+      float m_prev = -INFINITY;
+      if (j > 0) {
+        mbar_wait(bar(Cfg::BAR_TOKEN + (wg ^ 1) * 4 + w), ((j - 1) >> 1) & 1);
+        m_prev = mref[r];
+        if (m_prev != m_mine) {  // the other warpgroup advanced m: rebase my private row sum
+          if (l != 0.f) l *= fast_exp2((m_mine - m_prev) * c);
+          m_mine = m_prev;
+        }
+      }
       tmem_wait_ld();
       if ((threadIdx.x & 127) == 0) ev(wg, 2);
       if (j == n_kv - 1 && tail < 128) {
@@ -194,16 +205,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       const float mblk = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
                                fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-      // ---- serial section: take the reference maximum from the owner of block j-1, decide, publish ----
+      // ---- serial section: decide the reference maximum of this block and publish it ----
       if (j == 0) {
         m_mine = mblk;  // nothing accumulated yet
       } else {
-        mbar_wait(bar(Cfg::BAR_TOKEN + (wg ^ 1) * 4 + w), ((j - 1) >> 1) & 1);
-        const float m_prev = mref[r];
-        if (m_prev != m_mine) {  // the other warpgroup advanced m: rebase my private row sum
-          if (l != 0.f) l *= fast_exp2((m_mine - m_prev) * c);
-          m_mine = m_prev;
-        }
         const float m_new = fmaxf(m_prev, mblk);
         const bool need = (m_new - m_prev) * c > AP_RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, need)) {
@@ -230,10 +235,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) mbar_arrive(bar(Cfg::BAR_TOKEN + wg * 4 + w));
       if ((threadIdx.x & 127) == 0) ev(wg, 3);
 
-      // ---- exponentials: P = 2^(s*c - m*c) -> bf16 over the first 64 columns of the score buffer ----
+      // ---- exponentials: P = 2^(s*c - m*c) -> bf16 over the first 64 columns of the score buffer; the private row
+      //      sum rides along on the FMA pipe (the phase is bound by the 16-lane/clk exponential unit) ----
       const float neg = -m_mine * c;
       const float2 c2 = make_float2(c, c);
       const float2 neg2 = make_float2(neg, neg);
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (q == 2) {
@@ -255,8 +262,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             pv.x = fast_exp2(x.x);
             pv.y = fast_exp2(x.y);
           }
-          s[q * 32 + 2 * e] = __float_as_uint(pv.x);
-          s[q * 32 + 2 * e + 1] = __float_as_uint(pv.y);
+          acc[e & 3] = __fadd2_rn(acc[e & 3], pv);
           pk[e] = pack_bf16x2(pv.x, pv.y);
         }
         tmem_st_x16(t_s + q * 16, pk);
@@ -266,17 +272,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) arrive_issuer(pready_bar(buf, 1));
       if ((threadIdx.x & 127) == 0) ev(wg, 4);
-      // private row sum, off the critical path
-      float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll
-      for (int i = 0; i < 128; i += 8) {
-        a0 = __fadd2_rn(a0, make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
-        a1 = __fadd2_rn(a1, make_float2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
-        a2 = __fadd2_rn(a2, make_float2(__uint_as_float(s[i + 4]), __uint_as_float(s[i + 5])));
-        a3 = __fadd2_rn(a3, make_float2(__uint_as_float(s[i + 6]), __uint_as_float(s[i + 7])));
-      }
-      a0 = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
-      l += a0.x + a0.y;
+      acc[0] = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
+      l += acc[0].x + acc[0].y;
       // next block of this warpgroup: j + 2
       buf += 2;
       if (buf >= 3) { buf -= 3; sphase ^= 1; }
@@ -505,12 +502,14 @@ int launch_attn_pair(int cg, int emu, bool trace, int B, int Sq, int H, cudaStre
     switch (emu) {
       case 0: MV_AP(1, 0);
       case 4: MV_AP(1, 4);
+      case 6: MV_AP(1, 6);
       case 8: MV_AP(1, 8);
     }
   } else if (cg == 2) {
     switch (emu) {
       case 0: MV_AP(2, 0);
       case 4: MV_AP(2, 4);
+      case 6: MV_AP(2, 6);
       case 8: MV_AP(2, 8);
     }
   }

@@ -364,7 +364,15 @@ extern "C" int mova_b200_linear_ex(const void* A, int64_t lda, int seg_k, int64_
                "mova_b200_linear: residual epilogue needs a 16B-aligned residual with ldr >= N, ldr %% 8 == 0");
   }
   if (M == 0) return 0;
-  if (cta_group == 0) cta_group = 1;  // measured on B200: 128x256 single-CTA tiles 1.28 PF/s vs 0.73 for the pair
+  if (cta_group == 0) {
+    // Chosen per shape.  Measured on B200 (profiles/r02_gemm_vs_cublas.jsonl): the 256 x 256 CTA-pair tile runs at
+    // 1.42-1.51 PFLOP/s against 1.31-1.32 for the 128 x 256 single-CTA tile on the 360p video shapes (each SM reads half
+    // the B operand from shared memory and the pair loads 2/3 of the bytes per FLOP from L2 -- on a power-capped part
+    // that is clock), and is >= cuBLASLt on 8 of the 9 shapes timed.  Problems that do not fill the GPU with
+    // single-CTA tiles (the 403-token audio tower, the text keys) keep the smaller tile for parallelism.
+    const long long tiles1 = static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * ((N + GEMM_BN - 1) / GEMM_BN);
+    cta_group = (tiles1 >= sm_count()) ? 2 : 1;
+  }
   MV_REQUIRE(cta_group == 1 || cta_group == 2, "mova_b200_linear: cta_group must be 0, 1 or 2");
 
   CUtensorMap tmA, tmB, tmC;
