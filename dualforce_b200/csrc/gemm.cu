@@ -12,7 +12,10 @@
 //     main loop of tile i+1,
 //   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue
 //     (TMEM -> registers -> bias / GELU / gated residual -> bf16 -> swizzled smem -> TMA store),
-//   * tiles are walked in N-panels of 8 tiles so the weight panel and the A rows stay L2 resident.
+//   * tiles are walked in N-panels sized so that the weight panel (<= 48 MB) stays L2 resident while the activations
+//     stream past it once per panel; TMA loads of W carry the L2 evict_last hint, the C stores evict_first (ncu of the
+//     round-1 kernel: 8.3-9.3 GB of DRAM traffic per QKV GEMM against 1.9 GB algorithmic -- DRAM joules are clock on a
+//     power-capped part).
 #include "common.cuh"
 #include "host_utils.h"
 #include "../../include/mova_b200.h"
@@ -23,7 +26,6 @@ constexpr int GEMM_BM = 128;  // rows per CTA
 constexpr int GEMM_BN = 256;  // columns per tile
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_PANEL = 8;  // n-tiles per L2 panel
 constexpr int GEMM_STAGING_BYTES = 128 * 64 * 2;
 
 template <int CG>
@@ -52,14 +54,16 @@ struct GemmParams {
   long long ldr;
   const float* gate;  // [N] or null
   float scale;
+  int panel;  // n-tiles per L2 panel
 };
 
-__device__ __forceinline__ void gemm_decode_tile(int tile, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
-  const int per_panel = m_tiles * GEMM_PANEL;
+__device__ __forceinline__ void gemm_decode_tile(int tile, int m_tiles, int n_tiles, int panel_w, int& m_blk,
+                                                 int& n_blk) {
+  const int per_panel = m_tiles * panel_w;
   const int panel = tile / per_panel;
   const int within = tile - panel * per_panel;
-  const int n_begin = panel * GEMM_PANEL;
-  const int pw = min(GEMM_PANEL, n_tiles - n_begin);
+  const int n_begin = panel * panel_w;
+  const int pw = min(panel_w, n_tiles - n_begin);
   m_blk = within / pw;
   n_blk = n_begin + (within - m_blk * pw);
 }
@@ -134,7 +138,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         int m_blk, n_blk;
-        gemm_decode_tile(tile, m_tiles, n_tiles, m_blk, n_blk);
+        gemm_decode_tile(tile, m_tiles, n_tiles, p.panel, m_blk, n_blk);
         const int row0 = m_blk * GEMM_BM * CG + static_cast<int>(rank) * GEMM_BM;
         const int col0 = n_blk * GEMM_BN + static_cast<int>(rank) * Cfg::B_ROWS;
         int k_in_seg = 0, seg = 0;
@@ -146,12 +150,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             tma_load_3d(sA, &tmA, full_bar(stage), k_in_seg, row0, seg);
-            tma_load_2d(sB, &tmB, full_bar(stage), kb * GEMM_BK, col0);
+            tma_load_2d_hint(sB, &tmB, full_bar(stage), kb * GEMM_BK, col0, L2_EVICT_LAST);
           } else {
             const uint32_t leader_full = mapa_shared(full_bar(stage), 0);
             if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
             tma_load_3d_pair(sA, &tmA, leader_full, k_in_seg, row0, seg);
-            tma_load_2d_pair(sB, &tmB, leader_full, kb * GEMM_BK, col0);
+            tma_load_2d_pair_hint(sB, &tmB, leader_full, kb * GEMM_BK, col0, L2_EVICT_LAST);
           }
           k_in_seg += GEMM_BK;
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -198,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t chunk_counter = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tile_iter) {
       int m_blk, n_blk;
-      gemm_decode_tile(tile, m_tiles, n_tiles, m_blk, n_blk);
+      gemm_decode_tile(tile, m_tiles, n_tiles, p.panel, m_blk, n_blk);
       const int row0 = m_blk * GEMM_BM * CG + static_cast<int>(rank) * GEMM_BM;
       const int n0 = n_blk * GEMM_BN;
       const uint32_t acc = tile_iter & 1;
@@ -272,7 +276,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         named_bar_sync(1, 128);
         if (et == 0) {
           const int cseg = ncol0 / p.seg_n;
-          tma_store_3d(&tmC, buf, ncol0 - cseg * p.seg_n, row0, cseg);
+          tma_store_3d_hint(&tmC, buf, ncol0 - cseg * p.seg_n, row0, cseg, L2_EVICT_FIRST);
           tma_store_commit();
         }
       }
@@ -390,6 +394,13 @@ extern "C" int mova_b200_linear_ex(const void* A, int64_t lda, int seg_k, int64_
   p.ldr = ldr;
   p.gate = gate;
   p.scale = scale;
+  // n-tiles per panel: the panel's rows of W (panel x 256 x K bf16) should sit in L2 (126 MB, shared with the streaming
+  // operands) while all M-tiles pass: <= 48 MB -> 16 tiles at K = 5120, 6 at K = 13824
+  {
+    const long long per_tile = 2LL * GEMM_BN * K;
+    long long pw = (48LL << 20) / per_tile;
+    p.panel = static_cast<int>(pw < 2 ? 2 : (pw > 16 ? 16 : pw));
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
 #define MV_GEMM_DISPATCH(CGV)                                                                           \

@@ -365,21 +365,38 @@ class RotaryEmbedding(nn.Module):
         inv_freq = 1.0 / (base ** (torch.arange(0, dim, 2, dtype=torch.int64).to(device=device, dtype=torch.float) / dim))
         self.register_buffer("inv_freq", inv_freq, persistent=False)
         self.original_inv_freq = self.inv_freq
+        self.rope_precision = "fp32"
+
+    ROPE_PRECISIONS = ("fp32", "reference_bf16")
 
     @torch.no_grad()
     def forward(self, x, position_ids):
-        # Recomputed in fp32 on every (memoised) call instead of read from the buffer: ``module.to(torch.bfloat16)``
-        # -- how the reference loads its bf16 checkpoint -- also rounds the ``inv_freq`` buffer to bf16, which
-        # perturbs every RoPE frequency by up to 2^-9 (0.8 rad at audio position 400).  The fp32 oracle, and a model
-        # trained with fp32 buffers, use the exact frequencies; so does this path (deviations).
+        """Two precisions, selected by ``self.rope_precision`` (``install(pipe, bridge_rope=...)``):
+
+        ``"fp32"`` -- exact frequencies and tables: what the reference computes when it runs in fp32 (the CPU oracle).
+        ``"reference_bf16"`` -- what the reference computes when it runs the way it is shipped: ``from_pretrained(...,
+        torch_dtype=bfloat16)`` casts the non-persistent ``inv_freq`` buffer to bf16 (interactionv2.py:21-23), which
+        perturbs every frequency by up to 2^-9 (0.8 rad at audio position 400), and ``build_aligned_freqs`` is called
+        with the model dtype, so cos / sin are rounded to bf16 as well (:36, pipeline_mova.py:641-648).  Training
+        (mova_train.py:914) and inference both run that way, so a MOVA checkpoint has only ever seen the rounded
+        tables -- this mode reproduces them bit for bit (pinned by tests/golden/bridge_rope_bf16.npz).
+
+        The frequencies are recomputed from the formula on every (memoised) call instead of read from the buffer, so
+        the result does not depend on what ``.to(dtype)`` did to the module."""
+        if self.rope_precision not in self.ROPE_PRECISIONS:
+            raise ValueError(f"rope_precision must be one of {self.ROPE_PRECISIONS}, got {self.rope_precision!r}")
         inv_freq = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.int64).to(
             device=x.device, dtype=torch.float) / self.dim))
+        if self.rope_precision == "reference_bf16":
+            inv_freq = inv_freq.to(torch.bfloat16).float()
         inv = inv_freq[None, :, None].float().expand(position_ids.shape[0], -1, 1)
         pos = position_ids[:, None, :].float()
         freqs = (inv.float() @ pos.float()).transpose(1, 2)
         emb = torch.cat((freqs, freqs), dim=-1)
         cos = emb.cos() * self.attention_scaling
         sin = emb.sin() * self.attention_scaling
+        if self.rope_precision == "reference_bf16":
+            cos, sin = cos.to(torch.bfloat16).float(), sin.to(torch.bfloat16).float()
         return cos.to(dtype=x.dtype), sin.to(dtype=x.dtype)
 
 
@@ -580,7 +597,7 @@ class DualTowerConditionalBridge(nn.Module):
         device = torch.device(device) if device is not None else next(self.parameters()).device
         dtype = dtype or torch.float32
         key = (float(video_fps), f_v, h, w, L_a, str(device), dtype, float(self.audio_fps),
-               bool(self.apply_first_frame_bias_in_rope))
+               bool(self.apply_first_frame_bias_in_rope), self.rotary.rope_precision)
         hit = self._freq_cache.get(key)
         if hit is not None:
             return hit
@@ -604,6 +621,17 @@ class DualTowerConditionalBridge(nn.Module):
             self._freq_cache.pop(next(iter(self._freq_cache)))
         self._freq_cache[key] = out
         return out
+
+    @property
+    def bridge_rope(self) -> str:
+        """Precision of the aligned cross-RoPE tables: ``"fp32"`` or ``"reference_bf16"`` (RotaryEmbedding.forward)."""
+        return self.rotary.rope_precision
+
+    @bridge_rope.setter
+    def bridge_rope(self, value: str) -> None:
+        if value not in RotaryEmbedding.ROPE_PRECISIONS:
+            raise ValueError(f"bridge_rope must be one of {RotaryEmbedding.ROPE_PRECISIONS}, got {value!r}")
+        self.rotary.rope_precision = value
 
     def should_interact(self, layer_idx: int, direction: str) -> bool:
         return self.controller.should_interact(layer_idx, direction, self.interaction_mapping)

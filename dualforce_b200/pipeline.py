@@ -393,12 +393,18 @@ def _swap_blocks(model) -> int:
     return n
 
 
-def install(pipe, cuda_graph: bool = False) -> int:
+def install(pipe, cuda_graph: bool = False, bridge_rope: str = "reference_bf16") -> int:
     """Swap the B200 modules into a reference ``MOVA`` pipeline (or any object with ``video_dit``,
     ``video_dit_2``, ``audio_dit``, ``dual_tower_bridge``) in place, sharing its parameters, and bind
     ``pipe.forward_dual_tower_dit`` to the B200 path.  Returns the number of modules replaced -- the same idiom as
     ``MOVA.replace_attention`` (pipeline_mova.py:124-148), which becomes unnecessary (and must not be called after
     this): context parallelism is handled inside ``forward_dual_tower_dit`` from ``cp_mesh``.
+
+    ``bridge_rope``: precision of the bridge's aligned cross-RoPE tables.  ``"reference_bf16"`` (default) reproduces
+    what the reference computes when it runs as shipped -- bf16-rounded ``inv_freq`` and bf16 cos / sin tables
+    (interactionv2.py:21-23, 36), the only tables a MOVA checkpoint has been trained and sampled with; ``"fp32"``
+    keeps exact frequencies (what the reference computes in fp32; the CPU oracle's default).  See
+    ``modules.RotaryEmbedding.forward`` and INTEGRATION.md.
 
     Raises if the extension library is missing or the device is not sm_100 -- there is no fallback."""
     from . import _lib
@@ -410,6 +416,8 @@ def install(pipe, cuda_graph: bool = False) -> int:
         raise _lib.MovaB200Error("dualforce_b200.install: no CUDA device (the B200 path has no CPU fallback)")
     count = swap_modules(pipe)
     pipe.mova_b200_cuda_graph = bool(cuda_graph)
+    if getattr(pipe, "dual_tower_bridge", None) is not None:
+        pipe.dual_tower_bridge.bridge_rope = bridge_rope
     return count
 
 

@@ -137,6 +137,36 @@ def run_reference_step(cfg, seed):
     return {k: t.detach().numpy() for k, t in out.items()}, O.checksum(Pv, Pa, Pb, inp), keys
 
 
+BRIDGE_BF16_CFG = dict(O.TINY_CFG, grid_size=(9, 2, 2), audio_len=403)  # positions up to 402: the rounding matters
+
+
+@torch.no_grad()
+def run_reference_bridge_bf16(cfg, seed):
+    """The reference bridge run the way the reference runs it: ``bridge.to(torch.bfloat16)`` (what
+    ``from_pretrained(torch_dtype=bfloat16)`` does, rounding the non-persistent ``inv_freq`` buffer,
+    interactionv2.py:21-23) and ``build_aligned_freqs(dtype=bfloat16)`` (pipeline_mova.py:641-648), then one bridge
+    layer forward in bf16 on CPU.  Pins ``rope_precision="reference_bf16"`` of the oracle and of the product."""
+    Pv, Pa, Pb, inp = O.make_case(cfg, seed)
+    R, vis, aud, bridge, pipe = build_reference(cfg, Pv, Pa, Pb)
+    bridge = bridge.to(torch.bfloat16)
+    assert bridge.rotary.inv_freq.dtype == torch.bfloat16  # the cast reached the buffer
+    v_cs, a_cs = bridge.build_aligned_freqs(video_fps=cfg["video_fps"], grid_size=cfg["grid_size"],
+                                            audio_steps=cfg["audio_len"], device=torch.device("cpu"),
+                                            dtype=torch.bfloat16)
+    out = {"cos_v": v_cs[0], "sin_v": v_cs[1], "cos_a": a_cs[0], "sin_a": a_cs[1]}
+    xv, xa = inp["visual_x"].to(torch.bfloat16), inp["audio_x"].to(torch.bfloat16)
+    bv, ba = bridge(0, xv, xa, x_freqs=v_cs, y_freqs=a_cs, condition_scale=1.0, video_grid_size=cfg["grid_size"])
+    out["bridge0_visual"], out["bridge0_audio"] = bv, ba
+    # the same layer with the reference in fp32 (exact tables): how far the two precisions are apart
+    R2, _, _, bridge32, _ = build_reference(cfg, Pv, Pa, Pb)
+    v32, a32 = bridge32.build_aligned_freqs(video_fps=cfg["video_fps"], grid_size=cfg["grid_size"],
+                                            audio_steps=cfg["audio_len"], device=torch.device("cpu"), dtype=torch.float32)
+    bv32, ba32 = bridge32(0, inp["visual_x"], inp["audio_x"], x_freqs=v32, y_freqs=a32, condition_scale=1.0,
+                          video_grid_size=cfg["grid_size"])
+    out["bridge0_visual_fp32"], out["bridge0_audio_fp32"] = bv32, ba32
+    return {k: v.detach().float().numpy() for k, v in out.items()}, O.checksum(Pv, Pa, Pb, inp)
+
+
 def sample_indices(numel: int, n: int, seed: int = 0):
     """Fixed pseudo-random flat indices into a tensor of ``numel`` elements (shared by the generator and the tests)."""
     g = torch.Generator().manual_seed(seed)
@@ -164,9 +194,25 @@ def run_reference_reduced(cfg, seed):
     return {k: v.numpy() for k, v in out.items()}, O.checksum(Pv, Pa, Pb, inp)
 
 
+def write_bridge_bf16(out_dir):
+    arrays, csum = run_reference_bridge_bf16(BRIDGE_BF16_CFG, 31)
+    meta = dict(cfg=BRIDGE_BF16_CFG, seed=31, checksum=csum, torch=torch.__version__,
+                source="reference DualTowerConditionalBridge after .to(torch.bfloat16): build_aligned_freqs(dtype=bf16) "
+                       "tables and one bridge layer forward in bf16 on CPU (+ the same layer in fp32), by "
+                       "oracle/make_golden.py")
+    np.savez_compressed(os.path.join(out_dir, "bridge_rope_bf16.npz"), **arrays)
+    with open(os.path.join(out_dir, "bridge_rope_bf16.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    print("bridge_rope_bf16", {k: v.shape for k, v in arrays.items()}, "checksum", csum)
+
+
 def main():
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "bridge_bf16":  # only the newest fixture (the others are unchanged)
+        write_bridge_bf16(out_dir)
+        return
+    write_bridge_bf16(out_dir)
     for name, cfg, seed in (("tiny_dual_tower", O.TINY_CFG, 1234),):
         arrays, csum, keys = run_reference(cfg, seed)
         meta = dict(cfg=cfg, seed=seed, checksum=csum, torch=torch.__version__, reference_state_dict_keys=keys,

@@ -84,6 +84,12 @@ def main():
         mv, ma = run_check(rank, world)
         if rank == 0:
             print(f"cp_check OK world={world}", {"visual": mv, "audio": ma}, flush=True)
+        # an odd number of heads per rank (like the 5 of MOVA-360p at cp = 8): exchanged head by head, attended in
+        # two sets of head groups -- 3 heads per rank here
+        odd = dict(CP_CFG, visual_heads=3 * world, visual_dim=384 * world, visual_ffn=512 * world)
+        mv, ma = run_check(rank, world, cfg=odd, seed=78)
+        if rank == 0:
+            print(f"cp_check OK world={world} (3 heads per rank)", {"visual": mv, "audio": ma}, flush=True)
     finally:
         dist.destroy_process_group()
 

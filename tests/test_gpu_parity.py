@@ -272,6 +272,44 @@ def test_full_width_bridge_vs_oracle():
     _check_block(ba, ra, xa, "bridge v2a 1536<-5120")
 
 
+def test_bridge_rope_reference_bf16_mode_vs_reference_bf16_run():
+    """``bridge_rope="reference_bf16"`` on the device against the reference's own bf16 run of the bridge
+    (tests/golden/bridge_rope_bf16.npz: reference modules after ``.to(torch.bfloat16)``, 403 audio positions): the
+    tables are bit-identical to the reference's, the layer output tracks the reference's bf16 output, and the exact-
+    frequency mode is measurably further from it (the reference's rounded ``inv_freq`` moves the phases by up to
+    0.8 rad) -- while still matching the fp32 reference run."""
+    import dualforce_b200 as B
+    from test_oracle_golden import load_bridge_bf16_case
+
+    cfg, Pv, Pa, Pb, inp, gold = load_bridge_bf16_case()
+    bridge = B.DualTowerConditionalBridge(
+        visual_layers=cfg["visual_layers"], audio_layers=cfg["audio_layers"], visual_hidden_dim=cfg["visual_dim"],
+        audio_hidden_dim=cfg["audio_dim"], audio_fps=cfg["audio_fps"], head_dim=cfg["head_dim"],
+        interaction_strategy=cfg["interaction_strategy"], apply_cross_rope=True)
+    bridge.load_state_dict(Pb)
+    bridge.to("cuda", torch.bfloat16)
+    xv, xa = inp["visual_x"].to(torch.bfloat16), inp["audio_x"].to(torch.bfloat16)
+    kw = dict(video_fps=cfg["video_fps"], grid_size=cfg["grid_size"], audio_steps=cfg["audio_len"],
+              device=torch.device("cuda"), dtype=torch.float32)
+    errs = {}
+    for mode in ("reference_bf16", "fp32"):
+        bridge.bridge_rope = mode
+        gv, ga = bridge.build_aligned_freqs(**kw)
+        if mode == "reference_bf16":
+            assert torch.equal(ga[0].cpu(), gold["cos_a"]) and torch.equal(gv[1].cpu(), gold["sin_v"])
+        bv, ba = bridge(0, xv.cuda(), xa.cuda(), x_freqs=gv, y_freqs=ga, condition_scale=1.0)
+        for name, got, x in (("visual", bv, xv), ("audio", ba, xa)):
+            d = got.float().cpu() - x.float()
+            g16 = gold[f"bridge0_{name}"] - x.float()
+            g32 = gold[f"bridge0_{name}_fp32"] - x.float()
+            errs[(mode, name)] = (((d - g16).norm() / g16.norm()).item(), ((d - g32).norm() / g32.norm()).item())
+    # vs the reference's bf16 run: bf16 arithmetic noise on both sides in the matching mode, RoPE mismatch otherwise
+    assert errs[("reference_bf16", "audio")][0] < 0.04 and errs[("reference_bf16", "visual")][0] < 0.04, errs
+    assert errs[("fp32", "audio")][0] > 2 * errs[("reference_bf16", "audio")][0], errs
+    # vs the reference's fp32 run it is the other way round
+    assert errs[("fp32", "audio")][1] < 0.03 and errs[("fp32", "audio")][1] < errs[("reference_bf16", "audio")][1], errs
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_attention_properties_at_360p_size(ops):
     """BASELINE.json configs[1] geometry (L_v = 43120, head_dim 128), 2 of the 40 heads to bound memory/time:
