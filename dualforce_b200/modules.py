@@ -124,6 +124,18 @@ class _Packed:
         return self.w, self.b
 
 
+def prepack(module: nn.Module) -> None:
+    """Build every packed weight buffer below ``module`` NOW, on the current stream.  Packing frees the original
+    parameter storage (the Linears are re-pointed at views of the packed buffer), so it must not happen lazily on a
+    side stream while the allocating stream may recycle that storage: the context-parallel path calls this before it
+    forks the audio stream (found on hardware: a cold first forward with the audio side stream corrupted weights)."""
+    for m in module.modules():
+        if isinstance(m, SelfAttention):
+            m._qkv.get([m.q, m.k, m.v])
+        elif isinstance(m, (CrossAttention, ConditionalCrossAttention)):
+            m._kv.get([m.k, m.v])
+
+
 class AttentionModule(nn.Module):
     """wan_video_dit.py:154-161 -- ``forward(q, k, v)`` on flat ``[B, S, H*D]`` tensors."""
 

@@ -19,7 +19,7 @@ import torch
 
 from . import cp as cpmod
 from . import ops, rope
-from .modules import ConditionalCrossAttentionBlock, DiTBlock, DualTowerConditionalBridge, param_sig
+from .modules import ConditionalCrossAttentionBlock, DiTBlock, DualTowerConditionalBridge, param_sig, prepack
 
 __all__ = ["forward_dual_tower_dit", "install", "swap_modules", "CPRuntime", "GraphedForward"]
 
@@ -30,6 +30,8 @@ __all__ = ["forward_dual_tower_dit", "install", "swap_modules", "CPRuntime", "Gr
 class CPRuntime:
     """Process-group handle + the communication stream the all-to-alls are queued on."""
 
+    audio_side_stream = True  # class-level switch for A/B measurements and bisecting: False = everything on one stream
+
     def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: Optional[int] = None):
         self.group, self.rank, self.size, self.device = group, rank, size, device
         # head groups the Ulysses exchange is pipelined in when the heads per rank split evenly (2: measured in round 1
@@ -38,7 +40,7 @@ class CPRuntime:
         cuda = device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=device) if cuda else None
         # the replicated audio tower and the v2a bridge direction run here, beside the video block of the same layer
-        self.audio_stream = torch.cuda.Stream(device=device) if cuda else None
+        self.audio_stream = torch.cuda.Stream(device=device) if (cuda and self.audio_side_stream) else None
 
     @classmethod
     def from_mesh(cls, cp_mesh, device: torch.device, head_groups: Optional[int] = None) -> "CPRuntime":
@@ -267,6 +269,10 @@ def _forward_eager(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tens
             stream.wait_event(ev)
 
     if aud is not None:
+        # everything the audio stream will touch is built on the main stream first: packed weights re-point (and
+        # free) the original parameters, which belong to the main stream's allocator pool
+        prepack(audio_dit)
+        prepack(bridge)
         aud.wait_stream(main)
     ev_a = None  # audio_x of this layer is complete on the audio stream
     for i in range(min_layers):

@@ -272,6 +272,54 @@ def test_full_width_bridge_vs_oracle():
     _check_block(ba, ra, xa, "bridge v2a 1536<-5120")
 
 
+class _LoRAWrapped(torch.nn.Module):
+    """Stand-in with the attribute names of the reference's LoRALinear (engine/trainer/accelerate/lora_utils.py:19-90:
+    ``original_layer``, ``lora_A``, ``lora_B``, ``scaling``) -- what ``modules.merged_linear`` duck-types on; the real
+    class is exercised on CPU in tests/test_host_emulated.py (there is no reference tree on the GPU box)."""
+
+    def __init__(self, original_layer, rank, alpha, gen):
+        super().__init__()
+        self.original_layer = original_layer
+        self.scaling = alpha / rank
+        self.lora_A = torch.nn.Linear(original_layer.in_features, rank, bias=False)
+        self.lora_B = torch.nn.Linear(rank, original_layer.out_features, bias=False)
+        self.lora_A.weight.data = (torch.randn(self.lora_A.weight.shape, generator=gen) * 0.1).to(torch.bfloat16).float()
+        self.lora_B.weight.data = (torch.randn(self.lora_B.weight.shape, generator=gen) * 0.2).to(torch.bfloat16).float()
+
+
+def test_lora_adapters_are_folded_at_install_on_device():
+    """SURVEY 8f.4 on the device: a block whose q / k / v / o carry LoRA adapters (h = W x + (alpha / r) B A x,
+    mova_lora.py:147-188) is swapped with the adapters folded into the weights; the CUDA block matches the oracle
+    evaluated with the un-merged formula."""
+    import dualforce_b200 as B
+
+    cfg = O.TINY_CFG
+    Pv, Pa, Pb, inp = O.make_case(cfg, 5)
+    Pv, inp = bf16_round(Pv), bf16_round(inp)
+    host = B.DiTBlock(False, cfg["visual_dim"], cfg["visual_heads"], cfg["visual_ffn"], cfg["eps"])
+    host.load_state_dict({k[len("blocks.0."):]: v for k, v in Pv.items() if k.startswith("blocks.0.")})
+    gen = torch.Generator().manual_seed(9)
+    P_lora = dict(Pv)
+    for attn in ("self_attn", "cross_attn"):
+        mod = getattr(host, attn)
+        for name in ("q", "k", "v", "o"):
+            wrapped = _LoRAWrapped(getattr(mod, name), rank=4, alpha=8.0, gen=gen)
+            setattr(mod, name, wrapped)
+            key = f"blocks.0.{attn}.{name}.weight"
+            P_lora[key] = Pv[key] + wrapped.scaling * (wrapped.lora_B.weight.data @ wrapped.lora_A.weight.data)
+    host.to(torch.bfloat16)
+    mine = B.DiTBlock.from_reference(host).to("cuda")
+    assert isinstance(mine.self_attn.q, torch.nn.Linear) and isinstance(mine.cross_attn.o, torch.nn.Linear)
+    d = to_dev(inp)
+    got = mine(d["visual_x"], d["visual_context"], d["visual_t_mod"], d["visual_freqs"])
+    ref = O.dit_block(P_lora, "blocks.0", inp["visual_x"], inp["visual_context"], inp["visual_t_mod"], inp["visual_freqs"],
+                      cfg["visual_heads"], cfg["eps"])
+    plain = O.dit_block(Pv, "blocks.0", inp["visual_x"], inp["visual_context"], inp["visual_t_mod"], inp["visual_freqs"],
+                        cfg["visual_heads"], cfg["eps"])
+    assert (ref - plain).abs().max() > 0.05  # the adapters do change the output
+    assert_close(got, ref, "LoRA-merged block on the device vs un-merged oracle", ratio=2e-2, fro=8e-3)
+
+
 def test_bridge_rope_reference_bf16_mode_vs_reference_bf16_run():
     """``bridge_rope="reference_bf16"`` on the device against the reference's own bf16 run of the bridge
     (tests/golden/bridge_rope_bf16.npz: reference modules after ``.to(torch.bfloat16)``, 403 audio positions): the

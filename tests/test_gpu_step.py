@@ -239,15 +239,21 @@ def _cp_worker(rank, world, port):
         Pv, Pa, Pb, inp = O.make_step_case(cfg, 77)
         Pv, Pa, Pb = bf16_round(Pv), bf16_round(Pa), bf16_round(Pb)
         ctx = inp["context"].to(torch.bfloat16)
-        vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
-        kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"].cuda(), audio_latents=inp["audio_latents"].cuda(),
-                  context=ctx.cuda(), timestep=inp["timestep"].cuda(), audio_timestep=None, video_fps=cfg["video_fps"])
-        v, a = pipe.inference_single_step(**kw, cp_mesh=Mesh1D(dist.group.WORLD, rank, world))
-        torch.cuda.synchronize()
         rv, ra = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], ctx.float(),
                                          inp["timestep"])
-        assert_close(v, rv, f"cp{world} step visual (rank {rank})", ratio=3e-2, fro=1.5e-2)
-        assert_close(a, ra, f"cp{world} step audio (rank {rank})", ratio=3e-2, fro=1.5e-2)
+        # three cold starts (fresh towers: weights not packed yet, empty memos): the first context-parallel forward is
+        # where lazily built state meets the side streams (a weight-packing race showed up exactly here in round 2)
+        for rep in range(3):
+            vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
+            kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"].cuda(),
+                      audio_latents=inp["audio_latents"].cuda(), context=ctx.cuda(), timestep=inp["timestep"].cuda(),
+                      audio_timestep=None, video_fps=cfg["video_fps"])
+            v, a = pipe.inference_single_step(**kw, cp_mesh=Mesh1D(dist.group.WORLD, rank, world))
+            torch.cuda.synchronize()
+            assert_close(v, rv, f"cp{world} step visual (rank {rank}, cold start {rep})", ratio=3e-2, fro=1.5e-2)
+            assert_close(a, ra, f"cp{world} step audio (rank {rank}, cold start {rep})", ratio=3e-2, fro=1.5e-2)
+            v, a = pipe.inference_single_step(**kw, cp_mesh=Mesh1D(dist.group.WORLD, rank, world))  # warm memos
+            assert_close(a, ra, f"cp{world} step audio, warm (rank {rank}, {rep})", ratio=3e-2, fro=1.5e-2)
     finally:
         dist.destroy_process_group()
 
