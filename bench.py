@@ -303,6 +303,10 @@ def run_b200_arm(args):
     device = torch.device("cuda", local_rank)
     _lib.require_device(local_rank)
     cp_mesh = None
+    if args.cp_single_stream:
+        from dualforce_b200 import pipeline as _pl
+
+        _pl.CPRuntime.audio_side_stream = False
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
         from torch.distributed.device_mesh import init_device_mesh
@@ -496,6 +500,7 @@ def run_b200_arm(args):
                                     "(352x640x193f), L_a=403, 512 text tokens, random init")
                        if full else f"NOT the headline config (debug / BASELINE configs[3]): {cfg}",
                        "cp_size": world, "parallelism": f"cp{world}" if world > 1 else "single GPU",
+                       "cp_audio_side_stream": (not args.cp_single_stream) if world > 1 else None,
                        "video_experts_resident": experts,
                        "launch_mode": "cuda graph replay" if use_graph else "eager",
                        "l2_policy": "inputs+weights (~36 GB touched per forward) far exceed the 126 MB L2; no flush needed",
@@ -625,6 +630,8 @@ def main():
     ap.add_argument("--cuda-graph", type=int, default=0,
                     help="1: replay the forward as a CUDA graph, 0: eager launches (default)")
     ap.add_argument("--no-parity", action="store_true", help="debug: skip the configs[0] parity gate")
+    ap.add_argument("--cp-single-stream", action="store_true",
+                    help="A/B: run the replicated audio tower + v2a bridge on the main stream (the round-1 order)")
     ap.add_argument("--experts", type=int, default=None, help="resident video experts (default 2, as in the reference)")
     ap.add_argument("--schedule", type=int, default=0,
                     help="BASELINE configs[2]: time the whole N-step denoising loop (step.denoising_loop) as one region")

@@ -437,9 +437,10 @@ extern "C" int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q
              Skv, H);
   MV_REQUIRE(B <= 65535 && H <= 65535, "mova_b200_attn_fwd: B and H must fit a grid dimension");
   MV_REQUIRE(softmax_scale > 0.f, "mova_b200_attn_fwd: softmax_scale must be positive");
-  MV_REQUIRE(variant == 3 || variant == 91 || variant == 92, "mova_b200_attn_fwd_variant: variant must be 3 (round-1 "
-             "schedule), 91 (round-2 schedule, single CTA) or 92 (round-2 schedule, CTA pair); got %d", variant);
-  MV_REQUIRE(emu == 0 || emu == 4 || emu == 6 || emu == 8, "mova_b200_attn_fwd_variant: emu must be 0, 4, 6 or 8 (got %d)", emu);
+  MV_REQUIRE(variant == 3 || variant == 92, "mova_b200_attn_fwd_variant: variant must be 92 (round-2 schedule, CTA "
+             "pair) or 3 (round-1 schedule); got %d", variant);
+  MV_REQUIRE(emu == 4 || (variant == 3 && (emu == 0 || emu == 8)),
+             "mova_b200_attn_fwd_variant: exp2 emulation share must be 4 (variant 3 also has 0 and 8); got %d", emu);
   const int64_t row = static_cast<int64_t>(H) * D;
   MV_REQUIRE(q_ss >= row && k_ss >= row && v_ss >= row && o_ss >= row,
              "mova_b200_attn_fwd: sequence stride smaller than H*D");
@@ -452,14 +453,16 @@ extern "C" int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q
     v_bs = v_ss * Skv;
   }
 
-  // K box: 128 keys per load, or this CTA's 64 keys of the block in the CTA-pair kernel
-  const uint32_t k_box_rows = (variant == 92) ? 64 : 128;
+  // K / V boxes: one key block per load (K: this CTA's half of the block in the CTA-pair kernels)
+  const int bn = 128;
+  const int cg = (variant == 92) ? 2 : 1;
+  const uint32_t k_box_rows = static_cast<uint32_t>(bn / cg);
   // O box: the round-2 kernels store one 64-column panel per warpgroup
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = encode_tmap_3d(&tmQ, q, row, Sq, B, q_ss, q_bs, 64, 128, 1)) != 0) return rc;
   if ((rc = encode_tmap_3d(&tmK, k, row, Skv, B, k_ss, k_bs, 64, k_box_rows, 1)) != 0) return rc;
-  if ((rc = encode_tmap_3d(&tmV, v, row, Skv, B, v_ss, v_bs, 64, 128, 1)) != 0) return rc;
+  if ((rc = encode_tmap_3d(&tmV, v, row, Skv, B, v_ss, v_bs, 64, static_cast<uint32_t>(bn), 1)) != 0) return rc;
   if ((rc = encode_tmap_3d(&tmO, o, row, Sq, B, o_ss, o_bs, 64, 128, 1)) != 0) return rc;
 
   AttnParams p;
@@ -473,7 +476,7 @@ extern "C" int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q
 
   debug_attach();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant != 3) return launch_attn_pair(variant - 90, emu, trace != nullptr, B, Sq, H, st, tmQ, tmK, tmV, tmO, p);
+  if (variant != 3) return launch_attn_pair(cg, bn, emu, trace != nullptr, B, Sq, H, st, tmQ, tmK, tmV, tmO, p);
   dim3 grid((Sq + 255) / 256, H, B);
   if (trace != nullptr) return launch_attn<4, true>(grid, st, tmQ, tmK, tmV, tmO, p);
   switch (emu) {

@@ -38,7 +38,8 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 }
 
 
-int launch_attn_pair(int cg, int emu, bool trace, int B, int Sq, int H, cudaStream_t stream, const CUtensorMap& tmQ,
-                     const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p);
+int launch_attn_pair(int cg, int bn, int emu, bool trace, int B, int Sq, int H, cudaStream_t stream,
+                     const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
+                     const AttnParams& p);
 
 }  // namespace mv

@@ -45,11 +45,17 @@ constexpr int AP_PANEL_BYTES = 128 * 64 * 2;   // 128 rows of one 64-column (128
 constexpr uint32_t AP_TMEM_O = 384;            // S buffers at columns 0 / 128 / 256
 constexpr float AP_RESCALE_THRESHOLD = 8.0f;   // log2 units
 
-template <int CG>
+// BN: keys per block.  128 -> 3 score buffers, 96 -> 4 (the accumulator takes 128 of the 512 TMEM columns): with the
+// same tensor memory a fourth buffer lets Q.K^T run three blocks ahead of the softmax instead of two.
+template <int CG, int BN>
 struct APCfg {
-  static constexpr int SLOT_BYTES = AP_TILE_BYTES / CG;  // this CTA's part of the K (or V) tile of one key block
-  static constexpr int NS = 6 * CG;                      // ring slots
-  static constexpr int K_PANEL_BYTES = (128 / CG) * 128; // one 64-column panel of this CTA's K part
+  static_assert(BN == 128 || BN == 96, "key block must be 128 or 96");
+  static constexpr int NBUF = 384 / BN;                        // score buffers (columns [BN * i, BN * i + BN))
+  static constexpr int SLOT_BYTES = BN * 128 * 2 / CG;         // this CTA's part of the K (or V) tile of one key block
+  static constexpr int NS = 2 * NBUF * CG;                     // ring slots
+  static constexpr int K_PANEL_BYTES = (BN / CG) * 128;        // one 64-column panel of this CTA's K part
+  static constexpr int V_PANEL_BYTES = BN * 128;               // one 64-column panel of the V tile (all BN keys)
+  static constexpr int PV_KSTEPS = BN / 16;                    // tcgen05 K steps of P.V; the first 4 (64 keys) are part 0
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_KV = AP_TILE_BYTES;
   static constexpr int OFF_MREF = OFF_KV + NS * SLOT_BYTES;  // float[128]: reference maximum per query row
@@ -58,9 +64,9 @@ struct APCfg {
   static constexpr int BAR_QFULL = 0;
   static constexpr int BAR_KVFULL = 1;                  // [NS]
   static constexpr int BAR_KVEMPTY = BAR_KVFULL + NS;   // [NS]
-  static constexpr int BAR_SFULL = BAR_KVEMPTY + NS;    // [3]
-  static constexpr int BAR_PREADY = BAR_SFULL + 3;      // [3 score buffers][2 halves of the key block]
-  static constexpr int BAR_PVDONE = BAR_PREADY + 6;     // [2] (block parity)
+  static constexpr int BAR_SFULL = BAR_KVEMPTY + NS;    // [NBUF]
+  static constexpr int BAR_PREADY = BAR_SFULL + NBUF;   // [NBUF score buffers][2 parts of the key block]
+  static constexpr int BAR_PVDONE = BAR_PREADY + 2 * NBUF;  // [2] (block parity)
   static constexpr int BAR_TOKEN = BAR_PVDONE + 2;      // [2 warpgroups][4 warps]: "m of my block is published"
   static constexpr int NUM_BARS = BAR_TOKEN + 8;
   static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
@@ -87,12 +93,13 @@ __device__ __forceinline__ void umma_ts_cg(uint32_t d_tmem, uint32_t a_tmem, uin
 }
 
 // EMU: how many of every 16 score pairs take the polynomial exp2 (0 = all MUFU, 8 = half and half)
-template <int CG, int EMU, bool TRACE>
+template <int CG, int BN, int EMU, bool TRACE>
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                  const AttnParams p) {
-  using Cfg = APCfg<CG>;
+  using Cfg = APCfg<CG, BN>;
+  constexpr int NBUF = Cfg::NBUF;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,7 +108,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = (rank == 0);
   const int row0 = blockIdx.x * 128;  // this CTA's query tile (may lie entirely beyond Sq in the last pair)
-  const int n_kv = (p.Skv + 127) >> 7;
+  const int n_kv = (p.Skv + BN - 1) / BN;
 
   int trace_n = 0;
   const bool tracing = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && p.trace != nullptr;
@@ -128,7 +135,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(bar(Cfg::BAR_KVFULL + i), 1);   // the leader's expect_tx (covers both CTAs' bytes when CG == 2)
       mbar_init(bar(Cfg::BAR_KVEMPTY + i), 1);  // one tcgen05.commit
     }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < NBUF; ++i) {
       mbar_init(bar(Cfg::BAR_SFULL + i), 1);
       mbar_init(bar(Cfg::BAR_PREADY + 2 * i), 4 * CG);  // one arrive per softmax warp of the owning warpgroup(s)
       mbar_init(bar(Cfg::BAR_PREADY + 2 * i + 1), 4 * CG);
@@ -152,7 +159,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_sel = static_cast<uint32_t>(w * 32) << 16;
     const uint32_t t_o = tmem_base + lane_sel + AP_TMEM_O;
     const float c = p.scale_log2;
-    const int tail = p.Skv - (n_kv - 1) * 128;  // valid keys of the last block, 1..128
+    const int tail = p.Skv - (n_kv - 1) * BN;  // valid keys of the last block, 1..BN
     float m_mine = -INFINITY;  // the reference maximum (raw score units) my row sum l is expressed against
     float l = 0.f;
     // barrier addresses the softmax warps arrive on (the issuer lives in the leader CTA)
@@ -164,17 +171,17 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if constexpr (CG == 2) mbar_arrive_cluster(a); else mbar_arrive(a);
     };
 
-    int buf = wg;       // j % 3
-    int sphase = 0;     // (j / 3) & 1
+    int buf = wg;       // j % NBUF
+    int sphase = 0;     // (j / NBUF) & 1
 #pragma unroll 1
     for (int j = wg; j < n_kv; j += 2) {
-      const uint32_t t_s = tmem_base + lane_sel + buf * 128;
+      const uint32_t t_s = tmem_base + lane_sel + buf * BN;
       mbar_wait(bar(Cfg::BAR_SFULL + buf), sphase);
       tc_fence_after();
       if ((threadIdx.x & 127) == 0) ev(wg, 1);
-      uint32_t s[128];
+      uint32_t s[BN];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tmem_ld_x32(t_s + q * 32, reinterpret_cast<uint32_t(&)[32]>(s[q * 32]));
+      for (int q = 0; q < BN / 32; ++q) tmem_ld_x32(t_s + q * 32, reinterpret_cast<uint32_t(&)[32]>(s[q * 32]));
       // while the score tile is on its way from tensor memory: take the reference maximum published by the owner of
       // block j-1 (the other warpgroup, which passed this point most of a block ago)
       float m_prev = -INFINITY;
@@ -188,9 +195,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       tmem_wait_ld();
       if ((threadIdx.x & 127) == 0) ev(wg, 2);
-      if (j == n_kv - 1 && tail < 128) {
+      if (j == n_kv - 1 && tail < BN) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < BN; ++i)
           if (i >= tail) s[i] = 0xff800000u;  // -inf
       }
       // block maximum: 8 independent chains (the 3-input FMNMX has a long dependent-issue latency)
@@ -198,7 +205,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int k = 0; k < 8; ++k) mx[k] = fmaxf(__uint_as_float(s[k]), __uint_as_float(s[k + 8]));
 #pragma unroll
-      for (int i = 16; i < 128; i += 16) {
+      for (int i = 16; i < BN; i += 16) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           mx[k] = fmaxf(mx[k], fmaxf(__uint_as_float(s[i + k]), __uint_as_float(s[i + k + 8])));
@@ -242,9 +249,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float2 neg2 = make_float2(neg, neg);
       float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < BN / 32; ++q) {
         if (q == 2) {
-          // first half of P (keys 0..63) is complete: the issuer may start P.V on it
+          // first part of P (keys 0..63) is complete: the issuer may start P.V on it
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -276,7 +283,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l += acc[0].x + acc[0].y;
       // next block of this warpgroup: j + 2
       buf += 2;
-      if (buf >= 3) { buf -= 3; sphase ^= 1; }
+      if (buf >= NBUF) { buf -= NBUF; sphase ^= 1; }
     }
 
     // ---- both warpgroups: rebase to the final reference maximum, add the row sums ----
@@ -346,30 +353,30 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t dst = smem_base + Cfg::OFF_KV + slot * Cfg::SLOT_BYTES;
           const uint32_t full_local = bar(Cfg::BAR_KVFULL + slot);
           if constexpr (CG == 1) {
-            mbar_arrive_expect_tx(full_local, AP_TILE_BYTES);
+            mbar_arrive_expect_tx(full_local, Cfg::SLOT_BYTES);
             const CUtensorMap* m = is_v ? &tmV : &tmK;
-            tma_load_3d(dst, m, full_local, c0, blk * 128, b);
-            tma_load_3d(dst + AP_PANEL_BYTES, m, full_local, c0 + 64, blk * 128, b);
+            tma_load_3d(dst, m, full_local, c0, blk * BN, b);
+            tma_load_3d(dst + Cfg::V_PANEL_BYTES, m, full_local, c0 + 64, blk * BN, b);
           } else {
             const uint32_t full = mapa_shared(full_local, 0);
-            if (is_leader) mbar_arrive_expect_tx(full_local, AP_TILE_BYTES);  // 2 CTAs x 16 KB
+            if (is_leader) mbar_arrive_expect_tx(full_local, 2 * Cfg::SLOT_BYTES);  // both CTAs' parts
             if (is_v) {
-              // V part: all 128 keys, head-dim columns [64 rank, 64 rank + 64)  (B operand split along N = d)
-              tma_load_3d_pair(dst, &tmV, full, c0 + 64 * static_cast<int>(rank), blk * 128, b);
+              // V part: all BN keys, head-dim columns [64 rank, 64 rank + 64)  (B operand split along N = d)
+              tma_load_3d_pair(dst, &tmV, full, c0 + 64 * static_cast<int>(rank), blk * BN, b);
             } else {
-              // K part: keys [64 rank, 64 rank + 64) of the block, all 128 head-dim columns (B split along N = keys)
-              const int krow = blk * 128 + 64 * static_cast<int>(rank);
+              // K part: keys [BN/2 rank, BN/2 rank + BN/2) of the block, all 128 head-dim columns (B split along N = keys)
+              const int krow = blk * BN + (BN / 2) * static_cast<int>(rank);
               tma_load_3d_pair(dst, &tmK, full, c0, krow, b);
               tma_load_3d_pair(dst + Cfg::K_PANEL_BYTES, &tmK, full, c0 + 64, krow, b);
             }
           }
           if (++slot == Cfg::NS) { slot = 0; phase ^= 1; }
         };
-        const int n_pro = n_kv < 3 ? n_kv : 3;
+        const int n_pro = n_kv < NBUF ? n_kv : NBUF;
         for (int i = 0; i < n_pro; ++i) load_part(false, i);
         for (int j = 0; j < n_kv; ++j) {
           load_part(true, j);
-          if (j + 3 < n_kv) load_part(false, j + 3);
+          if (j + NBUF < n_kv) load_part(false, j + NBUF);
         }
       }
     } else if (warp_idx == 9) {
@@ -377,7 +384,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // The whole warp walks the schedule (addresses and descriptors live in uniform registers); one elected lane
       // issues the MMAs and commits.
       if (is_leader) {
-        constexpr uint32_t IDESC_QK = umma_idesc_bf16(128 * CG, 128, 0, 0);
+        constexpr uint32_t IDESC_QK = umma_idesc_bf16(128 * CG, BN, 0, 0);
         constexpr uint32_t IDESC_PV = umma_idesc_bf16(128 * CG, 128, 0, 1);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         auto commit = [&](uint32_t b_) {
@@ -394,19 +401,20 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int ks = 0; ks < 8; ++ks) {
               const uint32_t offq = ((ks >> 2) * AP_PANEL_BYTES + (ks & 3) * 32) >> 4;
               const uint32_t offk = ((ks >> 2) * Cfg::K_PANEL_BYTES + (ks & 3) * 32) >> 4;
-              umma_ss<CG>(tmem_u + buf * 128, qd + offq, kd + offk, IDESC_QK, ks > 0 ? 1u : 0u);
+              umma_ss<CG>(tmem_u + buf * BN, qd + offq, kd + offk, IDESC_QK, ks > 0 ? 1u : 0u);
             }
           }
           __syncwarp();
         };
-        // P.V over keys [64 half, 64 half + 64) of the block
+        // P.V over part 0 (keys 0..63: K steps 0-3) or part 1 (keys 64..BN-1) of the block
         auto issue_pv_half = [&](int buf, uint32_t vbase, int half, bool acc) {
-          const uint64_t vd = umma_desc_mn_sw128(vbase + half * 8192, AP_PANEL_BYTES, 1024);
+          const uint64_t vd = umma_desc_mn_sw128(vbase + half * 8192, Cfg::V_PANEL_BYTES, 1024);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              umma_ts_cg<CG>(tmem_u + AP_TMEM_O, tmem_u + buf * 128 + half * 32 + ks * 8, vd + ((ks * 2048) >> 4),
-                             IDESC_PV, (acc || half > 0 || ks > 0) ? 1u : 0u);
+              if (half * 4 + ks < Cfg::PV_KSTEPS)
+                umma_ts_cg<CG>(tmem_u + AP_TMEM_O, tmem_u + buf * BN + half * 32 + ks * 8, vd + ((ks * 2048) >> 4),
+                               IDESC_PV, (acc || half > 0 || ks > 0) ? 1u : 0u);
             }
           }
           __syncwarp();
@@ -416,7 +424,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         auto next_slot = [&]() { if (++slot == Cfg::NS) { slot = 0; phase ^= 1; } };
 
         mbar_wait(bar(Cfg::BAR_QFULL), 0);
-        const int n_pro = n_kv < 3 ? n_kv : 3;
+        const int n_pro = n_kv < NBUF ? n_kv : NBUF;
         for (int i = 0; i < n_pro; ++i) {
           mbar_wait(bar(Cfg::BAR_KVFULL + slot), phase);
           tc_fence_after();
@@ -425,7 +433,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           commit(bar(Cfg::BAR_KVEMPTY + slot));
           next_slot();
         }
-        int buf = 0, pphase = 0;  // j % 3, (j / 3) & 1
+        int buf = 0, pphase = 0;  // j % NBUF, (j / NBUF) & 1
         for (int j = 0; j < n_kv; ++j) {
           const uint32_t vslot = slot;
           mbar_wait(bar(Cfg::BAR_KVFULL + vslot), phase);
@@ -440,7 +448,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           commit(bar(Cfg::BAR_KVEMPTY + vslot));
           commit(bar(Cfg::BAR_PVDONE + (j & 1)));
           ev(2, 12 + (j & 1));
-          if (j + 3 < n_kv) {
+          if (j + NBUF < n_kv) {
             // the score buffer P(j) lived in is free once P.V(j) is queued (the tensor pipe runs in issue order)
             mbar_wait(bar(Cfg::BAR_KVFULL + slot), phase);
             tc_fence_after();
@@ -450,7 +458,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             next_slot();
             ev(2, 14 + (j & 1));
           }
-          if (++buf == 3) { buf = 0; pphase ^= 1; }
+          if (++buf == NBUF) { buf = 0; pphase ^= 1; }
         }
       }
     }
@@ -463,11 +471,11 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp_idx == 9) tmem_dealloc<CG>(tmem_base, 512);
 }
 
-template <int CG, int EMU, bool TRACE>
+template <int CG, int BN, int EMU, bool TRACE>
 static int launch_attn_pair_t(int B, int Sq, int H, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                               const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
-  using Cfg = APCfg<CG>;
-  auto kernel = attn_pair_kernel<CG, EMU, TRACE>;
+  using Cfg = APCfg<CG, BN>;
+  auto kernel = attn_pair_kernel<CG, BN, EMU, TRACE>;
   static bool configured[64] = {false};
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));
@@ -492,29 +500,21 @@ static int launch_attn_pair_t(int B, int Sq, int H, cudaStream_t stream, const C
   return 0;
 }
 
-// cg: 1 = single CTA per query tile, 2 = CTA pair;  emu: polynomial-exp2 share in 16ths of the score pairs (0, 4, 8)
-int launch_attn_pair(int cg, int emu, bool trace, int B, int Sq, int H, cudaStream_t stream, const CUtensorMap& tmQ,
-                     const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
-#define MV_AP(CGV, EMUV) \
-  return trace ? launch_attn_pair_t<CGV, EMUV, true>(B, Sq, H, stream, tmQ, tmK, tmV, tmO, p) \
-               : launch_attn_pair_t<CGV, EMUV, false>(B, Sq, H, stream, tmQ, tmK, tmV, tmO, p)
-  if (cg == 1) {
-    switch (emu) {
-      case 0: MV_AP(1, 0);
-      case 4: MV_AP(1, 4);
-      case 6: MV_AP(1, 6);
-      case 8: MV_AP(1, 8);
-    }
-  } else if (cg == 2) {
-    switch (emu) {
-      case 0: MV_AP(2, 0);
-      case 4: MV_AP(2, 4);
-      case 6: MV_AP(2, 6);
-      case 8: MV_AP(2, 8);
-    }
-  }
+// cg: 1 = single CTA per query tile, 2 = CTA pair;  bn: keys per block (128: 3 score buffers, 96: 4);
+// emu: polynomial-exp2 share in 16ths of the score pairs
+int launch_attn_pair(int cg, int bn, int emu, bool trace, int B, int Sq, int H, cudaStream_t stream,
+                     const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
+                     const AttnParams& p) {
+#define MV_AP(CGV, BNV, EMUV)                                                                              \
+  if (cg == CGV && bn == BNV && emu == EMUV)                                                               \
+    return trace ? launch_attn_pair_t<CGV, BNV, 4, true>(B, Sq, H, stream, tmQ, tmK, tmV, tmO, p)          \
+                 : launch_attn_pair_t<CGV, BNV, EMUV, false>(B, Sq, H, stream, tmQ, tmK, tmV, tmO, p)
+  // Instantiated: what ships.  Measured and dropped (profiles/r02_attn_schedules_call*.log, r02_attn_bn96_vs_bn128.log;
+  // 43120 x 43120 x 40 heads, sustained): CG = 1 1251-1273 TFLOP/s, BN = 96 / 4 score buffers 1259 (CG = 2) and 1152
+  // (CG = 1), exp2 emulation share 0 / 6 / 8 of 16: 1314 / 1224 / 1136, against 1325-1340 for CG = 2, BN = 128, share 4.
+  MV_AP(2, 128, 4);
 #undef MV_AP
-  set_error("launch_attn_pair: unsupported cta_group %d / exp2 emulation share %d", cg, emu);
+  set_error("launch_attn_pair: unsupported cta_group %d / key block %d / exp2 emulation share %d", cg, bn, emu);
   return -1;
 }
 

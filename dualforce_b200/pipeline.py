@@ -54,6 +54,24 @@ class CPRuntime:
 
 _RUNTIMES = {}
 
+# Optional per-segment device timeline (benchmarks/cp_layer_timeline.py): a list that receives
+# (segment name, stream name, start event, end event); None = off (the normal state: no events are created).
+TIMELINE = None
+
+
+@contextlib.contextmanager
+def _seg(name: str, stream_name: str = "main"):
+    if TIMELINE is None:
+        yield
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    try:
+        yield
+    finally:
+        e1.record()
+        TIMELINE.append((name, stream_name, e0, e1))
+
 
 def _cp_weights(block: DiTBlock, plan: cpmod.UlyssesPlan):
     """Destination-rank-major copies of the self-attention weights of ``block`` for ``plan``: built once per
@@ -95,12 +113,13 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
     Lc = h.shape[1]
     G, cp, wd = plan.groups, plan.cp, plan.w
     cos, sin = tables
-    send = ops.linear(h[0], w, b, out_segments=plan.nseg)  # [G*cp, Lc, 3*wd]
-    seg_stride = Lc * 3 * wd
-    ops.rmsnorm_rope_(send[0][:, 0:wd], nq, sa.norm_q.eps, head_dim=sa.head_dim, cos=cos, sin=sin,
-                      rope_mode=ops.ROPE_INTERLEAVED, segments=plan.nseg, seg_stride=seg_stride)
-    ops.rmsnorm_rope_(send[0][:, wd:2 * wd], nk, sa.norm_k.eps, head_dim=sa.head_dim, cos=cos, sin=sin,
-                      rope_mode=ops.ROPE_INTERLEAVED, segments=plan.nseg, seg_stride=seg_stride)
+    with _seg("qkv_gemm+qknorm_rope"):
+        send = ops.linear(h[0], w, b, out_segments=plan.nseg)  # [G*cp, Lc, 3*wd]
+        seg_stride = Lc * 3 * wd
+        ops.rmsnorm_rope_(send[0][:, 0:wd], nq, sa.norm_q.eps, head_dim=sa.head_dim, cos=cos, sin=sin,
+                          rope_mode=ops.ROPE_INTERLEAVED, segments=plan.nseg, seg_stride=seg_stride)
+        ops.rmsnorm_rope_(send[0][:, wd:2 * wd], nk, sa.norm_k.eps, head_dim=sa.head_dim, cos=cos, sin=sin,
+                          rope_mode=ops.ROPE_INTERLEAVED, segments=plan.nseg, seg_stride=seg_stride)
     send = send.view(G, cp, Lc, 3 * wd)
     comm = rt.comm_stream  # None for CPU tensors (gloo host-logic tests): same exchanges, program order
     main = torch.cuda.current_stream() if comm is not None else None
@@ -129,40 +148,49 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
     with on_comm():
         wait(comm, ready)
         for g in range(G):
-            cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
+            with _seg(f"all_to_all_in[{g}]", "comm"):
+                cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
             in_done.append(record(comm))
     out_done = []
     for gs, o in zip(sets, outs):
         # one attention launch per SET of consecutive head groups: the groups are its batch dimension (stride L*3*wd),
         # so a set starts as soon as its last group has landed while the next set is still on the wire
-        wait(main, in_done[gs[-1]])
+        with _seg(f"wait_all_to_all_in{gs}"):
+            wait(main, in_done[gs[-1]])
         qkv = recv[gs[0]:gs[-1] + 1]
-        ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=o)
+        with _seg(f"self_attention{gs}"):
+            ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=o)
         att = record(main)
         with on_comm():
             wait(comm, att)
-            for i, g in enumerate(gs):
-                cpmod.gather_heads(o[i], rows_per_rank, rt.rank, rt.group, out=back[g])
+            with _seg(f"all_to_all_out{gs}", "comm"):
+                for i, g in enumerate(gs):
+                    cpmod.gather_heads(o[i], rows_per_rank, rt.rank, rt.group, out=back[g])
             out_done.append(record(comm))
-    for ev in out_done:
-        wait(main, ev)
-    return ops.linear(back.view(G * cp, Lc, wd), wo, sa.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x[0], gate=gate,
-                      segments=plan.nseg).unsqueeze(0)
+    with _seg("wait_all_to_all_out"):
+        for ev in out_done:
+            wait(main, ev)
+    with _seg("o_proj"):
+        return ops.linear(back.view(G * cp, Lc, wd), wo, sa.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x[0], gate=gate,
+                          segments=plan.nseg).unsqueeze(0)
 
 
 def _video_block_cp(block: DiTBlock, x: torch.Tensor, context: torch.Tensor, t_mod: torch.Tensor, tables,
                     rt: CPRuntime, rows_per_rank: Sequence[int]) -> torch.Tensor:
     """DiTBlock.forward (wan_video_dit.py:275-291) on this rank's token chunk; only the self-attention communicates."""
-    mod = block.modulation_f32(t_mod)
-    ca = block.cross_attn
-    h = ops.layernorm(x, block.norm1.eps, shift=mod[0], scale=mod[1])
+    with _seg("modulation+ln1"):
+        mod = block.modulation_f32(t_mod)
+        ca = block.cross_attn
+        h = ops.layernorm(x, block.norm1.eps, shift=mod[0], scale=mod[1])
     x = _self_attention_cp(block, h, tables, x, mod[2], rt, rows_per_rank)
-    h = ops.layernorm(x, block.norm3.eps, weight=block.norm3.weight, bias=block.norm3.bias, out=h)
-    a = ca.attend(h, context)
-    ops.linear(a, ca.o.weight, ca.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x, out=x)
-    ops.layernorm(x, block.norm2.eps, shift=mod[3], scale=mod[4], out=h)
-    u = ops.linear(h, block.ffn[0].weight, block.ffn[0].bias, epilogue=ops.EPI_GELU_TANH)
-    ops.linear(u, block.ffn[2].weight, block.ffn[2].bias, epilogue=ops.EPI_RESIDUAL, residual=x, gate=mod[5], out=x)
+    with _seg("text_cross_attention"):
+        h = ops.layernorm(x, block.norm3.eps, weight=block.norm3.weight, bias=block.norm3.bias, out=h)
+        a = ca.attend(h, context)
+        ops.linear(a, ca.o.weight, ca.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x, out=x)
+    with _seg("ffn"):
+        ops.layernorm(x, block.norm2.eps, shift=mod[3], scale=mod[4], out=h)
+        u = ops.linear(h, block.ffn[0].weight, block.ffn[0].bias, epilogue=ops.EPI_GELU_TANH)
+        ops.linear(u, block.ffn[2].weight, block.ffn[2].bias, epilogue=ops.EPI_RESIDUAL, residual=x, gate=mod[5], out=x)
     return x
 
 
@@ -285,14 +313,18 @@ def _forward_eager(self, visual_dit, visual_x: torch.Tensor, audio_x: torch.Tens
         a2v = bridge.should_interact(i, "a2v")
         if a2v:
             # a2v: local video queries x replicated audio keys -- no communication
-            x_loc = bridge.audio_to_video_conditioners[str(i)].forward_residual(
-                x_pre, a_pre, v_cs_loc, a_cs, scale_for(a2v_condition_scale))
+            with _seg("bridge_a2v"):
+                x_loc = bridge.audio_to_video_conditioners[str(i)].forward_residual(
+                    x_pre, a_pre, v_cs_loc, a_cs, scale_for(a2v_condition_scale))
         with on_audio():
             wait(aud, ev_v)
+            side = "audio" if aud is not None else "main"
             if a2v and bridge.should_interact(i, "v2a"):
-                audio_x = _v2a_cp(bridge.video_to_audio_conditioners[str(i)], a_pre, x_pre, a_cs, v_cs_loc,
-                                  scale_for(v2a_condition_scale), rt)
-            audio_x = audio_dit.blocks[i](audio_x, audio_context, audio_t_mod, a_tab)  # replicated
+                with _seg("bridge_v2a(+all_gathers)", side):
+                    audio_x = _v2a_cp(bridge.video_to_audio_conditioners[str(i)], a_pre, x_pre, a_cs, v_cs_loc,
+                                      scale_for(v2a_condition_scale), rt)
+            with _seg("audio_block", side):
+                audio_x = audio_dit.blocks[i](audio_x, audio_context, audio_t_mod, a_tab)  # replicated
             ev_a = record(aud)
         x_loc = _video_block_cp(visual_dit.blocks[i], x_loc, visual_context, visual_t_mod, v_tab_loc, rt, rows)
     wait(main, ev_a)

@@ -89,10 +89,9 @@ int mova_b200_attn_fwd(const void* q, int64_t q_bs, int64_t q_ss, const void* k,
 
 /*
  * Development / measurement entry: the same attention with the schedule chosen explicitly.
- *   variant 92: round-2 schedule, CTA pair (cta_group::2)  -- what mova_b200_attn_fwd runs
- *   variant 91: round-2 schedule, single CTA per 128-row query tile
- *   variant  3: round-1 schedule (two query tiles per CTA, S/P aliased)
- *   emu: share of the exponentials evaluated as a polynomial on the FMA pipe, in 16ths of the score pairs (0, 4, 8)
+ *   variant 92: round-2 schedule, CTA pair (cta_group::2)  -- what mova_b200_attn_fwd runs for long key sequences
+ *   variant  3: round-1 schedule (two query tiles per CTA)   -- what it runs for <= 8 key blocks against many queries
+ *   emu: share of the exponentials evaluated as a polynomial on the FMA pipe, in 16ths of the score pairs (4)
  *   trace: NULL, or device memory for 3 x 4096 u64 event records (clock << 8 | id) of CTA (0,0,0)
  */
 int mova_b200_attn_fwd_variant(const void* q, int64_t q_bs, int64_t q_ss, const void* k, int64_t k_bs, int64_t k_ss,

@@ -1,5 +1,5 @@
-"""-m gpu: every attention schedule the library carries -- 92 (round-2 kernel, CTA pair: the shipped one), 91 (same,
-single CTA) and 3 (round-1 kernel, kept for A/B timing) -- against the CPU oracle through ``ops.attention(variant=...)``
+"""-m gpu: both attention schedules the library carries -- 92 (round-2 kernel, CTA pair: long key sequences) and 3
+(round-1 kernel: a handful of key blocks against many queries) -- forced on EVERY shape, against the CPU oracle through ``ops.attention(variant=...)``
 on ragged shapes (query / key counts that are not multiples of the 128-row tiles, odd tile counts so that the second
 CTA of the last pair is empty, a single key block so that warpgroup B has nothing to do, peaked scores that force the
 shared reference maximum to advance and the accumulator to be rescaled by either warpgroup).  Timing comparisons live
@@ -22,8 +22,7 @@ def _rand(shape, seed, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("variant", [92, 91, 3])
-@pytest.mark.parametrize("emu", [0, 4, 8])
+@pytest.mark.parametrize("variant,emu", [(92, 4), (3, 4), (3, 0), (3, 8)])
 def test_attention_variants_vs_oracle(variant, emu):
     import dualforce_b200 as B
 
@@ -36,7 +35,7 @@ def test_attention_variants_vs_oracle(variant, emu):
         assert (lse.cpu() - ref_lse).abs().max() <= 2e-3 * max(1.0, ref_lse.abs().max().item())
 
 
-@pytest.mark.parametrize("variant", [92, 91])
+@pytest.mark.parametrize("variant", [92, 3])
 def test_reference_maximum_advances_late(variant):
     """Keys sorted so that the row maximum keeps growing by more than the lazy-rescale threshold (2^8) from block to
     block: every block takes the rescale path, alternately in warpgroup A and B, and the private row sums must be
