@@ -464,14 +464,14 @@ def run_b200_arm(args):
     roofline = None
     if sel:
         avg_ms = sum(t for t, _ in sel) / len(sel)
-        tf = sel[0][1] / (avg_ms * 1e-3) / 1e12
+        tf = sum(f_ for _, f_ in sel) / (sum(t for t, _ in sel) * 1e-3) / 1e12  # launches may differ in heads (cp sets)
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "attn_traffic.json")
         if world == 1 and full and os.path.exists(tpath):  # the ncu capture is of the 40-head single-GPU launch
             with open(tpath) as fh:
                 tj = json.load(fh)
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-        roofline = {"bound": "tensor", "kernel": "attn_fwd_kernel (video self-attention, L_v x L_v, %d heads/launch)" % sel_heads(attn_events, L_v),
+        roofline = {"bound": "tensor", "kernel": "attn_pair_kernel<2,128,4> (video self-attention, L_v x L_v, %s heads x batch per launch)" % sel_heads(attn_events, L_v),
                     "achieved": tf, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": tf / peaks["sustained"],
                     "peak_kind": f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
                     "frac_of_burst_peak": tf / peaks["burst"], "frac_of_nominal_2250": tf / 2250.0,
@@ -588,10 +588,8 @@ def run_schedule(args, pipe, cfg, host, ctx, cp_mesh, device, world, rank, timed
 
 
 def sel_heads(events, L_v):
-    for (_, _, b, sq, skv, hh, dd) in events:
-        if sq == L_v and skv == L_v:
-            return hh
-    return 0
+    kinds = sorted({b * hh for (_, _, b, sq, skv, hh, dd) in events if sq == L_v and skv == L_v})
+    return "/".join(str(k) for k in kinds) if kinds else "0"
 
 
 _JSON_FD = None

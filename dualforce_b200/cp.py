@@ -99,15 +99,16 @@ def head_group_sets(heads_per_rank: int, want: int = 2):
 
     The exchange buffers are laid out in equal head groups (a constraint of the segmented GEMM operands).  When the
     heads split evenly in ``want`` groups, every group is one exchange and one attention launch (20 heads -> 2 x 10,
-    10 -> 2 x 5: the round-1 configuration).  An odd count (cp = 8: 5 heads per rank) is exchanged head by head and
-    attended in two sets of consecutive groups -- ``[[0, 1, 2], [3, 4]]`` -- each set being one attention launch with
-    the groups as its batch dimension, so the second set travels while the first is in the tensor cores and the
-    first set's outputs return while the second is attended."""
+    10 -> 2 x 5: the round-1 configuration).  An odd count (cp = 8: 5 heads per rank) is exchanged and attended head
+    by head -- ``[[0], [1], [2], [3], [4]]`` -- with the attention launches alternating between two side streams, so
+    only the first head's inbound and the last head's outbound exchange are exposed and the partial last wave of one
+    launch (337 query tiles on 148 SMs) overlaps the first wave of the next.  Measured at cp = 8 with the sets
+    ``[[0, 1, 2], [3, 4]]`` on one stream (profiles/r02_timeline_cp8.json): 0.44 + 0.10 + 0.24 ms of exposed exchange per
+    video layer, 10 % of the forward."""
     g = UlyssesPlan.pick_groups(heads_per_rank, want)
     if g >= min(want, heads_per_rank) or heads_per_rank < 3:
         return g, [[i] for i in range(g)]
-    first = (heads_per_rank + 1) // 2
-    return heads_per_rank, [list(range(0, first)), list(range(first, heads_per_rank))]
+    return heads_per_rank, [[i] for i in range(heads_per_rank)]
 
 
 def all_to_all_rows(inp: torch.Tensor, in_rows: Sequence[int], out_rows: Sequence[int],

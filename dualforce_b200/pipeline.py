@@ -41,6 +41,8 @@ class CPRuntime:
         self.comm_stream = torch.cuda.Stream(device=device) if cuda else None
         # the replicated audio tower and the v2a bridge direction run here, beside the video block of the same layer
         self.audio_stream = torch.cuda.Stream(device=device) if (cuda and self.audio_side_stream) else None
+        # more than two attention sets per layer (odd head count per rank): launches alternate between these
+        self.attn_streams = [torch.cuda.Stream(device=device) for _ in range(2)] if cuda else []
 
     @classmethod
     def from_mesh(cls, cp_mesh, device: torch.device, head_groups: Optional[int] = None) -> "CPRuntime":
@@ -152,15 +154,19 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
                 cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
             in_done.append(record(comm))
     out_done = []
-    for gs, o in zip(sets, outs):
+    side = rt.attn_streams if (comm is not None and len(sets) > 2) else []
+    for idx, (gs, o) in enumerate(zip(sets, outs)):
         # one attention launch per SET of consecutive head groups: the groups are its batch dimension (stride L*3*wd),
-        # so a set starts as soon as its last group has landed while the next set is still on the wire
-        with _seg(f"wait_all_to_all_in{gs}"):
-            wait(main, in_done[gs[-1]])
+        # so a set starts as soon as its last group has landed while the next set is still on the wire.  With more than
+        # two sets the launches alternate between two side streams: the partial last wave of one overlaps the next.
+        st = side[idx % len(side)] if side else main
         qkv = recv[gs[0]:gs[-1] + 1]
-        with _seg(f"self_attention{gs}"):
-            ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=o)
-        att = record(main)
+        with (torch.cuda.stream(st) if side else contextlib.nullcontext()):
+            with _seg(f"wait_all_to_all_in{gs}", "attn" if side else "main"):
+                wait(st, in_done[gs[-1]])
+            with _seg(f"self_attention{gs}", "attn" if side else "main"):
+                ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=o)
+            att = record(st)
         with on_comm():
             wait(comm, att)
             with _seg(f"all_to_all_out{gs}", "comm"):
