@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmova_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); mirrors include/mova_b200.h one to one
 SIGNATURES = {
@@ -63,6 +63,12 @@ SIGNATURES = {
     "mova_b200_cfg_euler": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
     "mova_b200_gemv_f32": (
         c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mova_b200_peer_alloc": (c_int, [c_int64, c_void_p, c_void_p]),
+    "mova_b200_peer_open": (c_int, [c_void_p, c_void_p]),
+    "mova_b200_peer_close": (c_int, [c_void_p]),
+    "mova_b200_peer_free": (c_int, [c_void_p]),
+    "mova_b200_peer_push": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "mova_b200_peer_wait": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p]),
 }
 
 EPI_BIAS, EPI_GELU_TANH, EPI_RESIDUAL = 0, 1, 2

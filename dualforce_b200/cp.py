@@ -94,20 +94,29 @@ class UlyssesPlan:
         return torch.cat(idx)
 
 
-def head_group_sets(heads_per_rank: int, want: int = 2):
+def head_group_sets(heads_per_rank: int, want: int = 2, set_sizes: Optional[Sequence[int]] = None):
     """(number of head groups, attention sets) for the pipelined Ulysses exchange of ``heads_per_rank`` heads.
 
     The exchange buffers are laid out in equal head groups (a constraint of the segmented GEMM operands).  When the
     heads split evenly in ``want`` groups, every group is one exchange and one attention launch (20 heads -> 2 x 10,
-    10 -> 2 x 5: the round-1 configuration).  An odd count (cp = 8: 5 heads per rank) is exchanged and attended head
-    by head -- ``[[0], [1], [2], [3], [4]]`` -- with the attention launches alternating between two side streams, so
-    only the first head's inbound and the last head's outbound exchange are exposed and the partial last wave of one
-    launch (337 query tiles on 148 SMs) overlaps the first wave of the next.  Measured at cp = 8 with the sets
-    ``[[0, 1, 2], [3, 4]]`` on one stream (profiles/r02_timeline_cp8.json): 0.44 + 0.10 + 0.24 ms of exposed exchange per
-    video layer, 10 % of the forward."""
+    10 -> 2 x 5: the round-1 configuration).  An odd count (cp = 8: 5 heads per rank) is exchanged head by head and
+    attended in SETS of consecutive heads, one attention launch per set (the heads are its batch dimension), the
+    launches alternating between two side streams so the partial last wave of one launch (337 query tiles on 148 SMs)
+    overlaps the first wave of the next.  ``set_sizes`` partitions the heads (``(1, 3, 1)`` -> ``[[0], [1, 2, 3], [4]]``:
+    a short first set so attention starts after one head has landed, a short last set so little of the return exchange
+    is exposed); ``None`` = one set per head, the configuration measured with the NCCL exchange
+    (profiles/r02_timeline_cp8.json)."""
     g = UlyssesPlan.pick_groups(heads_per_rank, want)
     if g >= min(want, heads_per_rank) or heads_per_rank < 3:
         return g, [[i] for i in range(g)]
+    if set_sizes is not None:
+        if sum(set_sizes) != heads_per_rank or min(set_sizes) < 1:
+            raise ValueError(f"attention set sizes {tuple(set_sizes)} do not partition {heads_per_rank} heads")
+        sets, i = [], 0
+        for n in set_sizes:
+            sets.append(list(range(i, i + n)))
+            i += n
+        return heads_per_rank, sets
     return heads_per_rank, [[i] for i in range(heads_per_rank)]
 
 

@@ -31,6 +31,13 @@ class CPRuntime:
     """Process-group handle + the communication stream the all-to-alls are queued on."""
 
     audio_side_stream = True  # class-level switch for A/B measurements and bisecting: False = everything on one stream
+    # Data path of the Ulysses exchange: "peer" = copy-engine pushes into the peers' windows + flag words
+    # (dualforce_b200/peer.py; falls back to NCCL with a warning when the windows cannot be mapped), "nccl" =
+    # dist.all_to_all_single on the communication stream (round-1 path, kept for A/B measurements and CUDA graphs).
+    exchange = "peer"
+    # Attention sets when the heads per rank do not split in two groups (cp = 8: 5 heads), see cp.head_group_sets;
+    # None = (1, n - 2, 1) with the peer exchange, one set per head with NCCL.
+    set_sizes = None
 
     def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: Optional[int] = None):
         self.group, self.rank, self.size, self.device = group, rank, size, device
@@ -43,6 +50,27 @@ class CPRuntime:
         self.audio_stream = torch.cuda.Stream(device=device) if (cuda and self.audio_side_stream) else None
         # more than two attention sets per layer (odd head count per rank): launches alternate between these
         self.attn_streams = [torch.cuda.Stream(device=device) for _ in range(2)] if cuda else []
+        self._px = None  # PeerExchange, False once it proved unavailable (tests inject a shared-memory one)
+
+    def peer_exchange(self):
+        """The peer-memory exchange for this runtime, or None (NCCL path).  First use is collective."""
+        if self._px is None:
+            self._px = False
+            if self.exchange == "peer" and self.device.type == "cuda":
+                from . import peer
+
+                self._px = peer.make_cuda_exchange(self.group, self.rank, self.size, self.device) or False
+        if self._px is False or self.exchange != "peer":
+            return None
+        if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            return None  # epochs and window growth are host-side state: a captured graph keeps the NCCL exchange
+        return self._px
+
+    def attention_sets(self, heads_per_rank: int, peer: bool):
+        sizes = self.set_sizes
+        if sizes is None and peer and heads_per_rank >= 3:
+            sizes = (1, heads_per_rank - 2, 1)
+        return cpmod.head_group_sets(heads_per_rank, self.head_groups, sizes)
 
     @classmethod
     def from_mesh(cls, cp_mesh, device: torch.device, head_groups: Optional[int] = None) -> "CPRuntime":
@@ -109,7 +137,8 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
     RMSNorm + RoPE on the segmented buffer, per head group {all-to-all, attention, all-to-all back} with the
     exchanges on the communication stream, o-projection reading source-rank-major with the gated residual fused."""
     sa = block.self_attn
-    groups, sets = cpmod.head_group_sets(sa.num_heads // rt.size, rt.head_groups)
+    px = rt.peer_exchange()
+    groups, sets = rt.attention_sets(sa.num_heads // rt.size, px is not None)
     plan = cpmod.UlyssesPlan(sa.num_heads, sa.head_dim, rt.size, groups)
     w, b, nq, nk, wo = _cp_weights(block, plan)
     Lc = h.shape[1]
@@ -141,29 +170,43 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
             stream.wait_event(ev)
 
     ready = record(main)
-    # every buffer is allocated on the compute stream; the side stream only fills it between two events
     L = sum(rows_per_rank)
-    recv = torch.empty(G, L, 3 * wd, dtype=torch.bfloat16, device=h.device)
-    back = torch.empty(G, cp, Lc, wd, dtype=torch.bfloat16, device=h.device)
+    if px is not None:
+        # this rank's window: the peers write recv / back directly, flag words say when (dualforce_b200/peer.py)
+        recv, back = px.begin(G, L, 3 * wd, rows_per_rank, wd)
+    else:
+        # every buffer is allocated on the compute stream; the side stream only fills it between two events
+        recv = torch.empty(G, L, 3 * wd, dtype=torch.bfloat16, device=h.device)
+        back = torch.empty(G, cp, Lc, wd, dtype=torch.bfloat16, device=h.device)
     outs = [torch.empty(len(gs), L, wd, dtype=torch.bfloat16, device=h.device) for gs in sets]
     in_done = []
     with on_comm():
         wait(comm, ready)
         for g in range(G):
             with _seg(f"all_to_all_in[{g}]", "comm"):
-                cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
+                if px is not None:
+                    px.push_in(g, send[g], stream=comm)
+                else:
+                    cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
             in_done.append(record(comm))
     out_done = []
-    side = rt.attn_streams if (comm is not None and len(sets) > 2) else []
+    # Side streams for the attention launches: with more than two sets, or with a set of one or two heads (337 query
+    # tiles per head on 148 SMs leave a partial last wave that only a launch on ANOTHER stream can fill).
+    few = min(len(gs) * plan.Hg for gs in sets) <= 2
+    side = rt.attn_streams if (comm is not None and (len(sets) > 2 or (few and len(sets) > 1))) else []
     for idx, (gs, o) in enumerate(zip(sets, outs)):
         # one attention launch per SET of consecutive head groups: the groups are its batch dimension (stride L*3*wd),
-        # so a set starts as soon as its last group has landed while the next set is still on the wire.  With more than
-        # two sets the launches alternate between two side streams: the partial last wave of one overlaps the next.
+        # so a set starts as soon as its last group has landed while the next set is still on the wire.
         st = side[idx % len(side)] if side else main
         qkv = recv[gs[0]:gs[-1] + 1]
         with (torch.cuda.stream(st) if side else contextlib.nullcontext()):
             with _seg(f"wait_all_to_all_in{gs}", "attn" if side else "main"):
-                wait(st, in_done[gs[-1]])
+                if px is not None:
+                    if side:
+                        wait(st, ready)  # stream order behind this layer's QKV GEMM (and the previous layer)
+                    px.wait_in(gs[0], gs[-1], stream=st)
+                else:
+                    wait(st, in_done[gs[-1]])
             with _seg(f"self_attention{gs}", "attn" if side else "main"):
                 ops.attention(qkv[..., 0:wd], qkv[..., wd:2 * wd], qkv[..., 2 * wd:], plan.Hg, out=o)
             att = record(st)
@@ -171,11 +214,16 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
             wait(comm, att)
             with _seg(f"all_to_all_out{gs}", "comm"):
                 for i, g in enumerate(gs):
-                    cpmod.gather_heads(o[i], rows_per_rank, rt.rank, rt.group, out=back[g])
+                    if px is not None:
+                        px.push_out(g, o[i], stream=comm)
+                    else:
+                        cpmod.gather_heads(o[i], rows_per_rank, rt.rank, rt.group, out=back[g])
             out_done.append(record(comm))
     with _seg("wait_all_to_all_out"):
         for ev in out_done:
             wait(main, ev)
+        if px is not None:
+            px.wait_out(stream=main)
     with _seg("o_proj"):
         return ops.linear(back.view(G * cp, Lc, wd), wo, sa.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x[0], gate=gate,
                           segments=plan.nseg).unsqueeze(0)

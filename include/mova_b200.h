@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOVA_B200_ABI_VERSION 3
+#define MOVA_B200_ABI_VERSION 4
 
 /* epilogues of mova_b200_linear */
 #define MOVA_EPI_BIAS 0      /* C = A W^T + b                          nn.Linear                          */
@@ -183,6 +183,42 @@ int mova_b200_gemv_f32(const float* x, const void* W, int64_t ldw, const void* b
  */
 int mova_b200_cfg_euler(const void* posi, const void* nega, const float* sample, float* out, int64_t n,
                         float cfg_scale, float dsigma, void* stream);
+
+/* ---- context-parallel exchange over NVSwitch peer memory (no NCCL kernel on the data path) ---- */
+
+/*
+ * The Ulysses head <-> sequence all-to-all that yunchang's LongContextAttention performs inside USPAttention.forward
+ * (wan_video_dit.py:192-208; `dist.all_to_all_single` underneath) as copy-engine transfers into the peers' receive
+ * windows plus flag words, so the exchange of one head group proceeds while the attention kernel of the previous
+ * group occupies every SM (an NCCL all-to-all is a kernel and waits for SMs: measured 0.75-2.1 ms instead of
+ * 0.10-0.16 ms per head group at cp = 8).  These are the only entry points that own memory.
+ *
+ *   peer_alloc   cudaMalloc + zero-fill a window on the current device and export its 64-byte cudaIpcMemHandle_t
+ *   peer_open    map a window exported by another process of this node (enables peer access lazily);
+ *                the returned pointer is valid on the current device
+ *   peer_close / peer_free   undo peer_open / peer_alloc
+ */
+int mova_b200_peer_alloc(int64_t nbytes, void** ptr, void* handle64);
+int mova_b200_peer_open(const void* handle64, void** ptr);
+int mova_b200_peer_close(void* ptr);
+int mova_b200_peer_free(void* ptr);
+
+/*
+ * Enqueue on `stream`: n_copies x cudaMemcpyAsync(dst[i], src[i], nbytes[i]) (local or peer-mapped device pointers,
+ * contiguous chunks), then ONE kernel that stores `epoch` (> 0, increasing over the life of the windows) into each of
+ * the n_flags (<= 32) 8-byte flag words -- typically one word in every destination's window -- with release semantics
+ * at system scope.  A consumer that observes the flag observes the copied bytes.
+ */
+int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, const int64_t* nbytes, int n_flags,
+                        void* const* flags, int64_t epoch, void* stream);
+
+/*
+ * Enqueue on `stream` one kernel that returns once all n_flags consecutive 8-byte words at `flags` (this device's own
+ * window) hold a value >= epoch (acquire, system scope).  After timeout_ms without progress it writes
+ * {0x4d565057, flag index, epoch, value seen} to mova_b200_debug_record() and traps: a lost peer becomes a CUDA error
+ * on this rank instead of a hung device.
+ */
+int mova_b200_peer_wait(const void* flags, int n_flags, int64_t epoch, int timeout_ms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ class _Mesh:
         return self._world
 
 
-def _worker(rank, world, port, grid, heads, results):
+def _worker(rank, world, port, grid, heads, results, exchange="collective", set_sizes=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -54,12 +54,29 @@ def _worker(rank, world, port, grid, heads, results):
         ctx = inp["context"].to(torch.bfloat16)
         vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
         mesh = _Mesh(rank, world)
+        window = None
+        if exchange == "peer":
+            # the product's peer-memory exchange (dualforce_b200/peer.py: offsets, flag words, epochs) over a
+            # shared-memory stand-in for the CUDA IPC windows
+            from dualforce_b200 import peer, pipeline as pl
+            from shm_peer import ShmWindow
+
+            rt = pl.CPRuntime.from_mesh(mesh, torch.device("cpu"))
+            window = ShmWindow(rank, world, str(port))
+            rt._px = peer.PeerExchange(window, rank, world)
+            pl.CPRuntime.set_sizes = set_sizes
         kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"], audio_latents=inp["audio_latents"], context=ctx,
                   timestep=inp["timestep"], audio_timestep=None, video_fps=cfg["video_fps"])
         v1, a1 = pipe.inference_single_step(**kw)                 # cp = 1 on this rank
         emulated_ops.CALLS.clear()
         v2, a2 = pipe.inference_single_step(**kw, cp_mesh=mesh)   # cp = 2, head on the local chunk
         calls = dict(emulated_ops.CALLS)
+        same_as_collective = None
+        if window is not None:  # the same forward through dist.all_to_all_single: must agree bit for bit
+            rt.exchange = "nccl"
+            vb, ab = pipe.inference_single_step(**kw, cp_mesh=mesh)
+            rt.exchange = "peer"
+            same_as_collective = bool(torch.equal(vb, v2) and torch.equal(ab, a2))
         rv, ra = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], ctx.float(),
                                          inp["timestep"])
         # the forward-level API must still return full-length hidden states under CP
@@ -92,19 +109,14 @@ def _worker(rank, world, port, grid, heads, results):
         results[rank] = dict(sp_ok=sp_ok, reload_ok=reload_ok,
             cp_vs_oracle_v=metrics(v2, rv), cp_vs_oracle_a=metrics(a2, ra), cp_vs_cp1_v=metrics(v2, v1.float()),
             cp_vs_cp1_a=metrics(a2, a1.float()), shapes=(tuple(v2.shape), tuple(a2.shape), tuple(full_v.shape)),
-            calls=calls, v2=v2.float(), a2=a2.float())
+            calls=calls, v2=v2.float(), a2=a2.float(),
+            peer=None if window is None else dict(same_as_collective=same_as_collective, pushes=window.pushes, waits=window.waits, epoch=rt._px.epoch,
+                                                  generation=window.generation))
     finally:
         dist.destroy_process_group()
 
 
-# 60 tokens -> 30 + 30; 9 tokens -> 5 + 4 (ragged); 4 ranks: 18 tokens -> 5 + 5 + 5 + 3, one video head per rank;
-# 6 heads on 2 ranks: an odd head count per rank (like 5 at cp = 8): exchanged head by head, attended as sets [[0, 1], [2]]
-@pytest.mark.parametrize("world,grid,heads", [(2, (3, 4, 5), None), (2, (1, 3, 3), None), (2, (2, 3, 3), 4),
-                                              (4, (2, 3, 3), 4), (2, (2, 3, 3), 6)])
-def test_step_context_parallel_gloo(world, grid, heads):
-    mgr = mp.Manager()
-    results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), grid, heads, results), nprocs=world, join=True)
+def _check(results, world, grid, heads):
     assert len(results) == world
     f, h, w = grid
     dim = 256 if heads is None else 128 * heads
@@ -124,3 +136,32 @@ def test_step_context_parallel_gloo(world, grid, heads):
     # every rank ends with the same full-length outputs
     for rank in range(1, world):
         assert torch.equal(results[0]["v2"], results[rank]["v2"]) and torch.equal(results[0]["a2"], results[rank]["a2"])
+
+
+# 60 tokens -> 30 + 30; 9 tokens -> 5 + 4 (ragged); 4 ranks: 18 tokens -> 5 + 5 + 5 + 3, one video head per rank;
+# 6 heads on 2 ranks: an odd head count per rank (like 5 at cp = 8): exchanged head by head, attended as sets [[0, 1], [2]]
+@pytest.mark.parametrize("world,grid,heads", [(2, (3, 4, 5), None), (2, (1, 3, 3), None), (2, (2, 3, 3), 4),
+                                              (4, (2, 3, 3), 4), (2, (2, 3, 3), 6)])
+def test_step_context_parallel_gloo(world, grid, heads):
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), grid, heads, results), nprocs=world, join=True)
+    _check(results, world, grid, heads)
+
+
+# The same cases through the peer-memory exchange (copy pushes into the peers' windows + flag words instead of
+# all_to_all_single): ragged chunks, several head groups per rank, 4 ranks, and an odd head count per rank attended as
+# the sets [[0], [1], [2]] / [[0], [1, 2]] -- results must equal the collective path's, bit for bit on every rank.
+@pytest.mark.parametrize("world,grid,heads,set_sizes", [(2, (1, 3, 3), None, None), (4, (2, 3, 3), 4, None),
+                                                        (2, (2, 3, 3), 6, (1, 1, 1)), (2, (2, 3, 3), 6, (1, 2))])
+def test_step_context_parallel_peer_exchange(world, grid, heads, set_sizes):
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), grid, heads, results, "peer", set_sizes), nprocs=world, join=True)
+    _check(results, world, grid, heads)
+    video_layers = O.TINY_STEP_CFG["visual_layers"]
+    for rank in range(world):
+        p = results[rank]["peer"]
+        assert p["same_as_collective"], f"rank {rank}: peer exchange and all_to_all_single disagree"
+        # 4 context-parallel forwards through the windows, one exchange round (epoch) per video self-attention
+        assert p["epoch"] == 4 * video_layers and p["waits"] > 0 and p["pushes"] > 0 and p["generation"] >= 1, p

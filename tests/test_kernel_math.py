@@ -36,18 +36,23 @@ def test_gelu_tanh_sigmoid_form():
     assert np.abs(sig - ref).max() < 1e-12
 
 
-def test_bounded_softmax_overflow_budget():
-    """P <= 2^slack per element; the row sum over the longest specified sequence and the O accumulator (|v| up to
-    2^8) must stay far inside fp32 (2^127), and the skip test must be conservative: bound >= any score."""
-    src = open(os.path.join(CSRC, "attn.cu")).read()
-    slack = float(re.search(r"AT_BOUND_SLACK = ([0-9.]+)f", src).group(1))
+def _rescale_thresholds():
+    out = {}
+    for fn, name in (("attn.cu", "AT_RESCALE_THRESHOLD"), ("attn_pair.cu", "AP_RESCALE_THRESHOLD")):
+        src = open(os.path.join(CSRC, fn)).read()
+        out[fn] = float(re.search(name + r" = ([0-9.]+)f", src).group(1))
+    return out
+
+
+def test_lazy_rescale_overflow_budget():
+    """Both attention kernels only advance the reference maximum when a block maximum exceeds it by more than
+    2^threshold (log2 units): P <= 2^threshold per element, so the row sum over the longest specified sequence and the
+    O accumulator (|v| up to 2^8) must stay far inside fp32 (2^127) and bf16 P must not overflow (2^127 as well)."""
+    th = _rescale_thresholds()
+    assert th["attn.cu"] == th["attn_pair.cu"], th
     longest = 49 * 45 * 80  # 720p
-    assert slack + math.log2(longest) + 8 < 120
-    rng = np.random.default_rng(0)
-    q = rng.standard_normal((64, 128)).astype(np.float32)
-    k = rng.standard_normal((128, 128)).astype(np.float32) * 3
-    bound = np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(k, axis=1).max()
-    assert (q @ k.T <= bound * 1.001).all()
+    for t in th.values():
+        assert t + math.log2(longest) + 8 < 120
 
 
 def _bf16(x):
@@ -57,58 +62,52 @@ def _bf16(x):
     return r.view(np.float32)
 
 
-def _online_softmax(q, k, v, scale, bounded, threshold=8.0, slack=64.0):
-    """Tile-level model of csrc/attn.cu's softmax in float32: exp2 domain, lazy rescale, P rounded to bf16 before P.V,
-    optional bounded skip of the row maximum (reference point left stale while the Cauchy-Schwarz bound allows)."""
+def _online_softmax(q, k, v, scale, threshold, block=128):
+    """Tile-level model of the kernels' softmax in float32: exp2 domain, reference maximum advanced only past
+    ``threshold`` (0 = every block, the textbook form), P rounded to bf16 before P.V, row sum from the unrounded P."""
     c = np.float32(scale * 1.4426950408889634)
     Sq, D = q.shape
     o = np.zeros((Sq, D), np.float32)
     l = np.zeros(Sq, np.float32)
     m_used = np.full(Sq, -np.inf, np.float32)
-    qn_c = np.linalg.norm(q, axis=1).astype(np.float32) * c * np.float32(1.001)
-    skipped = 0
-    for j0 in range(0, k.shape[0], 128):
-        kb, vb = k[j0:j0 + 128], v[j0:j0 + 128]
+    rescales = 0
+    for j0 in range(0, k.shape[0], block):
+        kb, vb = k[j0:j0 + block], v[j0:j0 + block]
         s = (q @ kb.T).astype(np.float32)
-        kmax = np.float32(np.linalg.norm(kb, axis=1).max())
-        skip = bounded and j0 > 0 and bool(np.all(qn_c * kmax - m_used * c <= slack))
-        if skip:
-            skipped += 1
-        else:
-            m_new = np.maximum(m_used, s.max(axis=1))
-            if j0 == 0:
-                m_used = m_new
-            elif np.any((m_new - m_used) * c > threshold):
-                f = np.exp2((m_used - m_new) * c).astype(np.float32)
-                m_used, l, o = m_new, l * f, o * f[:, None]
+        m_new = np.maximum(m_used, s.max(axis=1))
+        if j0 == 0:
+            m_used = m_new
+        elif np.any((m_new - m_used) * c > threshold):  # warp-uniform vote in the kernels
+            f = np.exp2((m_used - m_new) * c).astype(np.float32)
+            m_used, l, o = m_new, l * f, o * f[:, None]
+            rescales += 1
         p = np.exp2(s * c - (m_used * c)[:, None]).astype(np.float32)
         l = l + p.sum(axis=1, dtype=np.float32)
         o = o + _bf16(p) @ vb
-    return o / l[:, None], m_used * np.float32(scale) + np.log(l), skipped
+    return o / l[:, None], m_used * np.float32(scale) + np.log(l), rescales
 
 
-def test_bounded_softmax_is_numerically_equivalent():
-    """The stale-reference-point softmax (bounded skip) against exact attention in float64 and against the same model
-    with the maximum taken in every block: same accuracy, although P grows to 2^20..2^40 on the way."""
+def test_lazy_rescale_softmax_is_numerically_equivalent():
+    """The lazily advanced reference point against exact attention in float64 and against the same model with the
+    maximum advanced in every block: same accuracy with far fewer accumulator rescales, including when late keys carry
+    much larger scores than the first block."""
+    th = _rescale_thresholds()["attn_pair.cu"]
     rng = np.random.default_rng(3)
     Sq, Skv, D = 64, 4096, 128
     q = _bf16(rng.standard_normal((Sq, D)))
     k = _bf16(rng.standard_normal((Skv, D)))
-    k[2000:2010] *= 2.5  # late, much larger scores: the reference point of block 0 goes stale by ~2^30
+    k[2000:2010] *= 2.5  # late, much larger scores
     v = _bf16(rng.standard_normal((Skv, D)))
     scale = 3.0 / math.sqrt(D)  # the self-test's sharpened scale
     s = (q.astype(np.float64) @ k.astype(np.float64).T) * scale
     pexact = np.exp(s - s.max(axis=1, keepdims=True))
     exact = (pexact / pexact.sum(axis=1, keepdims=True)) @ v.astype(np.float64)
     lse_exact = s.max(axis=1) + np.log(pexact.sum(axis=1))
-    o_plain, lse_plain, skipped_plain = _online_softmax(q, k, v, scale, bounded=False)
-    o_bound, lse_bound, skipped = _online_softmax(q, k, v, scale, bounded=True)
-    assert skipped_plain == 0 and skipped >= 28  # nearly every block after the first skips its maximum
-    err_plain = np.abs(o_plain - exact).max()
-    err_bound = np.abs(o_bound - exact).max()
-    assert err_bound <= 1.5 * err_plain + 1e-6 and err_bound < 1e-2, (err_plain, err_bound)  # bf16 rounding of P
-    assert np.abs(lse_bound - lse_exact).max() < 1e-3 and np.abs(lse_plain - lse_exact).max() < 1e-3
-    # inputs for which the bound is useless (huge norms): every block takes the exact path, same answer as plain
-    o_big, _, skipped_big = _online_softmax(q * 8, k, v, scale, bounded=True)
-    o_big_plain, _, _ = _online_softmax(q * 8, k, v, scale, bounded=False)
-    assert skipped_big == 0 and np.array_equal(o_big, o_big_plain)
+    o_every, lse_every, n_every = _online_softmax(q, k, v, scale, threshold=0.0)
+    o_lazy, lse_lazy, n_lazy = _online_softmax(q, k, v, scale, threshold=th)
+    assert n_lazy < n_every and n_lazy >= 1  # the late keys force at least one real rescale
+    err_every = np.abs(o_every - exact).max()
+    err_lazy = np.abs(o_lazy - exact).max()
+    # both are bf16-rounding-of-P noise (relative 2^-9 whatever the reference point): same order of magnitude
+    assert err_lazy <= 4 * err_every + 1e-6 and err_lazy < 1e-2, (err_every, err_lazy)
+    assert np.abs(lse_lazy - lse_exact).max() < 1e-3 and np.abs(lse_every - lse_exact).max() < 1e-3
