@@ -285,6 +285,16 @@ def nbytes(t):
     return t.numel() * t.element_size()
 
 
+def cp_exchange_used(pl) -> str:
+    """What the context-parallel runtimes of this process actually used for the Ulysses exchange."""
+    used = set()
+    for rt in pl._RUNTIMES.values():
+        px = getattr(rt, "_px", None)
+        used.add("peer windows (CUDA IPC, copy engines + flag words)" if (px and rt.exchange == "peer")
+                 else "nccl all_to_all_single")
+    return " / ".join(sorted(used)) if used else "none"
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -303,10 +313,13 @@ def run_b200_arm(args):
     device = torch.device("cuda", local_rank)
     _lib.require_device(local_rank)
     cp_mesh = None
-    if args.cp_single_stream:
-        from dualforce_b200 import pipeline as _pl
+    from dualforce_b200 import pipeline as _pl
 
+    if args.cp_single_stream:
         _pl.CPRuntime.audio_side_stream = False
+    _pl.CPRuntime.exchange = args.cp_exchange
+    if args.cp_sets:
+        _pl.CPRuntime.set_sizes = tuple(int(v) for v in args.cp_sets.split(","))
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
         from torch.distributed.device_mesh import init_device_mesh
@@ -501,6 +514,8 @@ def run_b200_arm(args):
                        if full else f"NOT the headline config (debug / BASELINE configs[3]): {cfg}",
                        "cp_size": world, "parallelism": f"cp{world}" if world > 1 else "single GPU",
                        "cp_audio_side_stream": (not args.cp_single_stream) if world > 1 else None,
+                       "cp_exchange": cp_exchange_used(_pl) if world > 1 else None,
+                       "cp_attention_sets": args.cp_sets or "default",
                        "video_experts_resident": experts,
                        "launch_mode": "cuda graph replay" if use_graph else "eager",
                        "l2_policy": "inputs+weights (~36 GB touched per forward) far exceed the 126 MB L2; no flush needed",
@@ -630,6 +645,10 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="debug: skip the configs[0] parity gate")
     ap.add_argument("--cp-single-stream", action="store_true",
                     help="A/B: run the replicated audio tower + v2a bridge on the main stream (the round-1 order)")
+    ap.add_argument("--cp-exchange", choices=["peer", "nccl"], default="peer",
+                    help="Ulysses exchange data path: copy-engine pushes into peer windows + flags (default), or NCCL "
+                         "all_to_all_single (round-1 path)")
+    ap.add_argument("--cp-sets", default="", help="A/B: attention set sizes for an odd head count per rank, e.g. 1,3,1")
     ap.add_argument("--experts", type=int, default=None, help="resident video experts (default 2, as in the reference)")
     ap.add_argument("--schedule", type=int, default=0,
                     help="BASELINE configs[2]: time the whole N-step denoising loop (step.denoising_loop) as one region")

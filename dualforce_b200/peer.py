@@ -238,13 +238,20 @@ class PeerExchange:
         self.window.wait(self.flag_index(1, 0, 0, cp), self._G * cp, self.epoch, stream)
 
 
+_EXCHANGES = {}  # one set of windows per (process group, device) for the life of the process
+
+
 def make_cuda_exchange(group, rank: int, size: int, device: torch.device) -> Optional[PeerExchange]:
-    """A ``PeerExchange`` over CUDA IPC windows, or ``None`` (with a warning, on every rank alike) when the windows
-    cannot be mapped -- the caller then keeps the NCCL all-to-all."""
-    px = PeerExchange(CudaIpcWindow(group, rank, size, device), rank, size)
-    try:
-        px.window.ensure(FLAG_BYTES + (1 << 20))  # collective probe: allocate, exchange handles, map every peer
-    except PeerUnavailable as e:
-        warnings.warn(f"dualforce_b200: peer-memory exchange unavailable, using NCCL all-to-all ({e})")
-        return None
-    return px
+    """The ``PeerExchange`` over CUDA IPC windows for ``group`` on ``device``, or ``None`` (with a warning, on every
+    rank alike) when the windows cannot be mapped -- the caller then keeps the NCCL all-to-all.  First call per group
+    is collective."""
+    key = (getattr(group, "group_name", None) or id(group), str(device), rank, size)
+    if key not in _EXCHANGES:
+        px = PeerExchange(CudaIpcWindow(group, rank, size, device), rank, size)
+        try:
+            px.window.ensure(FLAG_BYTES + (1 << 20))  # collective probe: allocate, exchange handles, map every peer
+        except PeerUnavailable as e:
+            warnings.warn(f"dualforce_b200: peer-memory exchange unavailable, using NCCL all-to-all ({e})")
+            px = None
+        _EXCHANGES[key] = px
+    return _EXCHANGES[key]

@@ -80,16 +80,29 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
+    from dualforce_b200 import pipeline as pl
+
     try:
-        mv, ma = run_check(rank, world)
-        if rank == 0:
-            print(f"cp_check OK world={world}", {"visual": mv, "audio": ma}, flush=True)
-        # an odd number of heads per rank (like the 5 of MOVA-360p at cp = 8): exchanged head by head, attended in
-        # two sets of head groups -- 3 heads per rank here
-        odd = dict(CP_CFG, visual_heads=3 * world, visual_dim=384 * world, visual_ffn=512 * world)
-        mv, ma = run_check(rank, world, cfg=odd, seed=78)
-        if rank == 0:
-            print(f"cp_check OK world={world} (3 heads per rank)", {"visual": mv, "audio": ma}, flush=True)
+        # both data paths of the Ulysses exchange: copy-engine pushes into peer windows + flag words (the default),
+        # and NCCL all_to_all_single
+        for exchange in ("peer", "nccl"):
+            pl.CPRuntime.exchange = exchange
+            pl._RUNTIMES.clear()
+            mv, ma = run_check(rank, world)
+            used = sorted({("peer" if (rt._px and rt.exchange == "peer") else "nccl") for rt in pl._RUNTIMES.values()})
+            if rank == 0:
+                print(f"cp_check OK world={world} exchange={exchange} used={used}", {"visual": mv, "audio": ma},
+                      flush=True)
+            # an odd number of heads per rank (like the 5 of MOVA-360p at cp = 8): exchanged head by head, attended in
+            # sets of head groups -- 3 heads per rank here ([[0], [1], [2]] on two side streams)
+            odd = dict(CP_CFG, visual_heads=3 * world, visual_dim=384 * world, visual_ffn=512 * world)
+            mv, ma = run_check(rank, world, cfg=odd, seed=78)
+            if rank == 0:
+                print(f"cp_check OK world={world} exchange={exchange} (3 heads per rank)", {"visual": mv, "audio": ma},
+                      flush=True)
+            if exchange == "peer" and used != ["peer"]:
+                raise SystemExit(f"rank {rank}: the peer-memory exchange was requested but {used} ran")
+        pl.CPRuntime.exchange = "peer"
     finally:
         dist.destroy_process_group()
 
