@@ -380,6 +380,10 @@ def run_b200_arm(args):
     audio = host["audio_latents"].to(device)
     lat_next, audio_next = torch.empty_like(lat_view, memory_format=torch.contiguous_format), torch.empty_like(audio)
     ctx = {w_: host[f"context_{w_}"].to(device) for w_ in ("pos", "neg")}  # uploaded once per video (:404-405)
+    if args.cfg_merge:
+        if world > 1:
+            raise SystemExit("--cfg-merge is single-GPU (context parallelism keeps the two-call CFG form)")
+        ctx["both"] = torch.cat([ctx["pos"], ctx["neg"]], dim=0)
     n_sched = max(args.schedule or 0, 50)
     timesteps, sigmas = flow_match_schedule(n_sched)
     ts_dev = [timesteps[i].reshape(1).to(device=device, dtype=torch.float32) for i in range(n_sched)]
@@ -393,8 +397,12 @@ def run_b200_arm(args):
         """2 x inference_single_step + CFG + Euler update of both latents (pipeline_mova.py:416-475)."""
         kw = dict(visual_dit=pipe.video_dit, visual_latents=x_in, audio_latents=a_in, timestep=ts, audio_timestep=None,
                   video_fps=cfg["video_fps"], cp_mesh=cp_mesh)
-        pos_v, pos_a = pipe.inference_single_step(context=ctx["pos"], **kw)
-        neg_v, neg_a = pipe.inference_single_step(context=ctx["neg"], **kw)
+        if args.cfg_merge:  # the reference's cfg_merge form (pipeline_mova.py:443-445): ONE B = 2 forward per step
+            out_v, out_a = pipe.inference_single_step(context=ctx["both"], **kw)
+            pos_v, neg_v, pos_a, neg_a = out_v[0:1], out_v[1:2], out_a[0:1], out_a[1:2]
+        else:
+            pos_v, pos_a = pipe.inference_single_step(context=ctx["pos"], **kw)
+            neg_v, neg_a = pipe.inference_single_step(context=ctx["neg"], **kw)
         bstep.guided_update(pos_v, neg_v, lat_in, cfg_scale, sig[idx], sig[idx + 1], out=lat_out)
         bstep.guided_update(pos_a, neg_a, a_in, cfg_scale, sig[idx], sig[idx + 1], out=a_out)
 
@@ -516,6 +524,7 @@ def run_b200_arm(args):
                        "cp_audio_side_stream": (not args.cp_single_stream) if world > 1 else None,
                        "cp_exchange": cp_exchange_used(_pl) if world > 1 else None,
                        "cp_attention_sets": args.cp_sets or "default",
+                       "cfg_form": "merged: one B=2 forward per step" if args.cfg_merge else "two B=1 forwards per step",
                        "video_experts_resident": experts,
                        "launch_mode": "cuda graph replay" if use_graph else "eager",
                        "l2_policy": "inputs+weights (~36 GB touched per forward) far exceed the 126 MB L2; no flush needed",
@@ -645,6 +654,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="debug: skip the configs[0] parity gate")
     ap.add_argument("--cp-single-stream", action="store_true",
                     help="A/B: run the replicated audio tower + v2a bridge on the main stream (the round-1 order)")
+    ap.add_argument("--cfg-merge", action="store_true",
+                    help="A/B: run the CFG pair as ONE batched forward (the reference's cfg_merge form), single GPU")
     ap.add_argument("--cp-exchange", choices=["peer", "nccl"], default="peer",
                     help="Ulysses exchange data path: copy-engine pushes into peer windows + flags (default), or NCCL "
                          "all_to_all_single (round-1 path)")

@@ -341,9 +341,11 @@ class DiTBlock(nn.Module):
         return ops.add_to_f32(self.modulation.to(dtype=torch.bfloat16), t_mod.to(torch.bfloat16)).reshape(6, self.dim)
 
     def forward(self, x: torch.Tensor, context: torch.Tensor, t_mod: torch.Tensor, freqs) -> torch.Tensor:
-        if x.shape[0] != 1:  # per-sample modulation: run the samples one by one
+        if x.shape[0] != 1 and t_mod.shape[0] != 1:  # per-sample modulation: run the samples one by one
             return torch.cat([self.forward(x[i:i + 1], context[i:i + 1], t_mod[i:i + 1], freqs)
                               for i in range(x.shape[0])], dim=0)
+        # B > 1 with ONE t_mod (the CFG pair of pipeline_mova.py:443-445: same latents and timestep, two prompts): the
+        # samples are extra rows of every GEMM / LayerNorm and the batch dimension of the attention launches
         mod = self.modulation_f32(t_mod)
         eps = self.norm1.eps
         sa, ca = self.self_attn, self.cross_attn

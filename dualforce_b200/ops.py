@@ -214,6 +214,15 @@ def rmsnorm_rope_(x: torch.Tensor, weight: torch.Tensor, eps: float, *, head_dim
     elements later (the destination-rank-major q/k/v buffer of the context-parallel path)."""
     _need(x, torch.bfloat16, "x")
     _need(weight, torch.bfloat16, "weight")
+    if rope_mode != ROPE_NONE and x.dim() == 3 and x.shape[0] > 1 and cos is not None:
+        width = head_dim // 2 if rope_mode == ROPE_INTERLEAVED else head_dim
+        if cos.numel() == x.shape[1] * width:
+            # a batch that shares one position table (CFG pair: the same tokens twice): one launch per sample, the table
+            # row is the token index inside the sample
+            for b in range(x.shape[0]):
+                rmsnorm_rope_(x[b], weight, eps, head_dim=head_dim, cos=cos, sin=sin, rope_mode=rope_mode,
+                              segments=segments, seg_stride=seg_stride)
+            return x
     L, seg_len, ldx = _rows2d(x, "x")
     d = seg_len * segments
     if weight.numel() != d or not weight.is_contiguous():

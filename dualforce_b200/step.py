@@ -130,8 +130,8 @@ class Head(nn.Module):
         if t_mod.dim() == 3:
             raise NotImplementedError("per-token time embedding (seperated_timestep, wan_video_dit.py:324-326) is not "
                                       "used by MOVA")
-        if x.shape[0] != 1 or t_mod.shape[0] != 1:
-            raise NotImplementedError("Head: batch > 1 (MOVA runs CFG as two B = 1 calls)")
+        if t_mod.shape[0] != 1:
+            raise NotImplementedError("Head: one time embedding per call (a CFG pair shares its timestep)")
         mod = ops.add_to_f32(self.modulation.to(dtype=torch.bfloat16), t_mod.to(torch.bfloat16).unsqueeze(1))
         mod = mod.reshape(2, self.dim)
         h = ops.layernorm(x, self.norm.eps, shift=mod[0], scale=mod[1])
@@ -189,9 +189,7 @@ class _Tower(nn.Module):
         return patchify(self, x)
 
     def unpatchify(self, x: torch.Tensor, grid_size):
-        if x.shape[0] != 1:
-            raise NotImplementedError("unpatchify: batch > 1")
-        return ops.unpatchify(x[0], grid_size, self.patch_size, self.out_dim).unsqueeze(0)
+        return torch.stack([ops.unpatchify(x[b], grid_size, self.patch_size, self.out_dim) for b in range(x.shape[0])])
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor, **kwargs) -> torch.Tensor:
@@ -288,18 +286,19 @@ def embed_text(model, context: torch.Tensor) -> torch.Tensor:
 def patchify(model, latents: torch.Tensor):
     """``model.patchify`` (wan_video_dit.py:399-409; wan_audio_dit.py:180-189): ``[1, C, F, H, W]`` (``[1, C, F]``)
     latents, fp32 or bf16 -> tokens ``[1, L, dim]`` bf16 and the token grid."""
-    if latents.shape[0] != 1:
-        raise NotImplementedError("patchify: batch > 1 (MOVA runs B = 1)")
     conv = model.patch_embedding
     w = conv.weight
     w2 = w.view(w.shape[0], -1) if w.is_contiguous() else w.reshape(w.shape[0], -1)
-    x = latents[0]
-    if x.dtype not in (torch.float32, torch.bfloat16):
-        x = x.to(torch.float32)
-    x = x.to(w.device).contiguous()
     psize = tuple(conv.kernel_size)
-    cols = ops.patchify(x, psize)
-    tokens = ops.linear(cols, w2, conv.bias).unsqueeze(0)
+    cols = []
+    for b in range(latents.shape[0]):  # B = 2 for a merged CFG pair (pipeline_mova.py:443-445), else 1
+        x = latents[b]
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.to(torch.float32)
+        x = x.to(w.device).contiguous()
+        cols.append(ops.patchify(x, psize))
+    cols = cols[0].unsqueeze(0) if len(cols) == 1 else torch.stack(cols)
+    tokens = ops.linear(cols, w2, conv.bias)
     if x.dim() == 2:
         grid = (x.shape[1] // psize[0],)
     else:
@@ -338,7 +337,7 @@ def head_unpatchify(model, x: torch.Tensor, t: torch.Tensor, grid, rows_per_rank
         y = cpmod.all_gather_cat(y, rows_per_rank, group, dim=1)
     psize = tuple(model.patch_embedding.kernel_size)
     out_ch = y.shape[-1] // math.prod(psize)
-    return ops.unpatchify(y[0], grid, psize, out_ch).unsqueeze(0)
+    return torch.stack([ops.unpatchify(y[b], grid, psize, out_ch) for b in range(y.shape[0])])
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -350,7 +349,12 @@ def inference_single_step(self, visual_dit, visual_latents: torch.Tensor, audio_
                           video_fps: float, cp_mesh=None):
     """Drop-in for ``MOVA.inference_single_step`` (pipeline_mova.py:500-609), same arguments and return value:
     ``(visual_output [1, 16, F, H/8, W/8], audio_output [1, 128, L_a])`` in bf16.  ``self`` needs ``audio_dit``,
-    ``dual_tower_bridge`` and ``forward_dual_tower_dit`` (a ``MOVA`` pipeline after ``dualforce_b200.install``)."""
+    ``dual_tower_bridge`` and ``forward_dual_tower_dit`` (a ``MOVA`` pipeline after ``dualforce_b200.install``).
+
+    ``context [B, 512, text_dim]`` with B = 2 runs the CFG pair as ONE batched forward (what the reference's
+    ``cfg_merge`` branch, pipeline_mova.py:443-445, expects back: outputs ``[2, ...]``, positive first): the two
+    samples share the timestep, so they are extra rows of every GEMM / LayerNorm and the batch dimension of every
+    attention launch; latents may be given once (``[1, ...]``) or per sample.  Single GPU only (cp_mesh=None)."""
     from . import pipeline as pl
 
     audio_dit = self.audio_dit
@@ -369,6 +373,16 @@ def inference_single_step(self, visual_dit, visual_latents: torch.Tensor, audio_
 
     visual_x, grid_size = patchify(visual_dit, visual_latents)
     audio_x, (f,) = patchify(audio_dit, audio_latents)
+    B = context.shape[0] if context.dim() == 3 else 1
+    if B > 1:
+        # merged CFG pair (the `cfg_merge` branch of pipeline_mova.py:443-445): ONE forward over [positive, negative]
+        # prompts.  Latents given once are shared by the samples: patchified once, tokens repeated.
+        if visual_x.shape[0] == 1:
+            visual_x = visual_x.repeat(B, 1, 1)
+        if audio_x.shape[0] == 1:
+            audio_x = audio_x.repeat(B, 1, 1)
+        if visual_x.shape[0] != B or audio_x.shape[0] != B:
+            raise ValueError(f"inference_single_step: {B} prompts but {visual_x.shape[0]} / {audio_x.shape[0]} latents")
     visual_freqs = token_freqs(visual_dit, grid_size, visual_x.device)
     audio_freqs = token_freqs(audio_dit, (f,), audio_x.device)
 
@@ -407,7 +421,7 @@ def guided_update(noise_pred_posi: torch.Tensor, noise_pred_nega: Optional[torch
 def denoising_loop(pipe, latents: torch.Tensor, condition: torch.Tensor, audio_latents: torch.Tensor,
                    prompt_embeds: torch.Tensor, negative_prompt_embeds: Optional[torch.Tensor], paired_timesteps,
                    timestep_to_sigma, video_fps: float, cfg_scale: float = 5.0, cp_mesh=None, pick_visual_dit=None,
-                   final_sigma: float = 0.0):
+                   final_sigma: float = 0.0, cfg_merge: bool = False):
     """The diffusion loop of ``MOVA.__call__`` (pipeline_mova.py:405-487) on the B200 step: per scheduler iteration
     two ``inference_single_step`` calls (one when ``cfg_scale == 1``), then CFG + ``step_from_to`` fused in
     ``guided_update``.  ``latents [1, 16, F, H, W]`` / ``audio_latents [1, 128, L_a]`` are the fp32 noise tensors,
@@ -417,13 +431,17 @@ def denoising_loop(pipe, latents: torch.Tensor, condition: torch.Tensor, audio_l
     expert switch (:407-413); default: ``pipe.video_dit``.  Returns the final fp32 ``(latents, audio_latents)``.
 
     The model input ``cat([latents, condition], dim=1)`` (:416) is one persistent buffer whose first 16 channels are
-    updated in place by the fused kernel, so no concatenation copy runs per step."""
+    updated in place by the fused kernel, so no concatenation copy runs per step.
+
+    ``cfg_merge=True`` (the reference's ``cfg_merge`` switch, :348, :443-445): the positive and the negative prompt
+    run as ONE batched ``inference_single_step`` (B = 2) per iteration instead of two calls; single GPU only."""
     dev = latents.device
     n_lat = latents.shape[1]
     model_input = torch.cat([latents.float(), condition.float()], dim=1).contiguous()  # once per video
     lat_view = model_input[:, :n_lat]
     audio = audio_latents.float().contiguous().clone()
     total = paired_timesteps.shape[0]
+    both = None
     for idx in range(total):
         t_v, t_a = paired_timesteps[idx]
         visual_dit = pick_visual_dit(float(t_v)) if pick_visual_dit is not None else pipe.video_dit
@@ -431,10 +449,17 @@ def denoising_loop(pipe, latents: torch.Tensor, condition: torch.Tensor, audio_l
         ts_a = t_a.reshape(1).to(device=dev, dtype=torch.float32)
         kw = dict(visual_dit=visual_dit, visual_latents=model_input, audio_latents=audio, timestep=ts_v,
                   audio_timestep=ts_a, video_fps=video_fps, cp_mesh=cp_mesh)
-        pos_v, pos_a = pipe.inference_single_step(context=prompt_embeds, **kw)
         neg_v = neg_a = None
-        if cfg_scale != 1.0:
-            neg_v, neg_a = pipe.inference_single_step(context=negative_prompt_embeds, **kw)
+        if cfg_merge and cfg_scale != 1.0:
+            if both is None:
+                both = torch.cat([prompt_embeds, negative_prompt_embeds], dim=0)  # once per video: keeps the memos warm
+            out_v, out_a = pipe.inference_single_step(context=both, **kw)
+            pos_v, neg_v = out_v[0:1], out_v[1:2]
+            pos_a, neg_a = out_a[0:1], out_a[1:2]
+        else:
+            pos_v, pos_a = pipe.inference_single_step(context=prompt_embeds, **kw)
+            if cfg_scale != 1.0:
+                neg_v, neg_a = pipe.inference_single_step(context=negative_prompt_embeds, **kw)
         nxt = paired_timesteps[idx + 1] if idx + 1 < total else None
         sig_v, sig_a = timestep_to_sigma(t_v), timestep_to_sigma(t_a)
         sig_v_to = timestep_to_sigma(nxt[0]) if nxt is not None else final_sigma

@@ -126,6 +126,11 @@ def layernorm(x, eps, *, weight=None, bias=None, shift=None, scale=None, out=Non
 
 
 def rmsnorm_rope_(x, weight, eps, *, head_dim=128, cos=None, sin=None, rope_mode=ROPE_NONE, segments=1, seg_stride=0):
+    if x.dim() == 3 and x.shape[0] > 1:  # a batch sharing one position table (CFG pair): sample by sample, like ops.py
+        for b in range(x.shape[0]):
+            rmsnorm_rope_(x[b], weight, eps, head_dim=head_dim, cos=cos, sin=sin, rope_mode=rope_mode, segments=segments,
+                          seg_stride=seg_stride)
+        return x
     _count("rmsnorm_rope_")
     _need(x, BF16, "x"); _need(weight, BF16, "weight")
     assert x.stride(-1) == 1

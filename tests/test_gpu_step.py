@@ -172,6 +172,46 @@ def test_inference_single_step_vs_oracle_and_golden():
     assert torch.equal(v, v3) and torch.equal(a, a3)
 
 
+def test_cfg_merged_step_equals_two_calls_on_device():
+    """SURVEY 8(f)2, the reference's `cfg_merge` branch (pipeline_mova.py:443-445): [positive, negative] prompts as ONE
+    B = 2 forward against the two B = 1 calls and the oracle.  The GEMM / LayerNorm / attention kernels compute every
+    row independently of the batch, so the halves agree with the single calls up to schedule choices that look at the batch size; the merged denoising
+    loop ends on the same latents."""
+    from dualforce_b200 import step
+
+    cfg, Pv, Pa, Pb, inp, gold = _step_case()
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb)
+    g = torch.Generator().manual_seed(5)
+    pos = inp["context"].to(torch.bfloat16)
+    neg = (torch.randn(pos.shape, generator=g) * 0.5).to(torch.bfloat16)
+    kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"].cuda(), audio_latents=inp["audio_latents"].cuda(),
+              timestep=inp["timestep"].cuda(), audio_timestep=None, video_fps=cfg["video_fps"])
+    pv, pa = pipe.inference_single_step(context=pos.cuda(), **kw)
+    nv, na = pipe.inference_single_step(context=neg.cuda(), **kw)
+    bv, ba = pipe.inference_single_step(context=torch.cat([pos, neg], dim=0).cuda(), **kw)
+    assert bv.shape == (2,) + tuple(pv.shape[1:]) and ba.shape == (2,) + tuple(pa.shape[1:])
+    # same kernels, same per-row arithmetic; only schedule choices that look at the batch (split-KV of the bridge
+    # attention, CTA-pair GEMM tiles) may differ, i.e. bf16 re-association noise at most
+    for got, want, name in ((bv[0:1], pv, "visual +"), (bv[1:2], nv, "visual -"), (ba[0:1], pa, "audio +"),
+                            (ba[1:2], na, "audio -")):
+        assert_close(got, want.float().cpu(), f"merged CFG step vs single call, {name}", ratio=8e-3, fro=3e-3)
+    rv, ra = O.inference_single_step(Pv, Pa, Pb, cfg, inp["visual_latents"], inp["audio_latents"], neg.float(),
+                                     inp["timestep"])
+    assert_close(bv[1:2], rv, "merged CFG step, negative half, visual vs oracle", ratio=3e-2, fro=1.5e-2)
+    assert_close(ba[1:2], ra, "merged CFG step, negative half, audio vs oracle", ratio=3e-2, fro=1.5e-2)
+    f, h, w = cfg["grid_size"]
+    latents = torch.randn(1, 16, f, 2 * h, 2 * w, generator=g).cuda()
+    condition = torch.randn(1, 20, f, 2 * h, 2 * w, generator=g).cuda()
+    audio = torch.randn(1, cfg["audio_in_dim"], cfg["audio_len"], generator=g).cuda()
+    sched = O.PairScheduler(num_inference_steps=3)
+    args = (pipe, latents, condition, audio, pos.cuda(), neg.cuda(), sched.get_pairs(), sched.timestep_to_sigma,
+            cfg["video_fps"])
+    two_v, two_a = step.denoising_loop(*args, cfg_scale=5.0)
+    one_v, one_a = step.denoising_loop(*args, cfg_scale=5.0, cfg_merge=True)
+    assert_close(one_v, two_v.cpu(), "merged CFG loop vs two-call loop, video latents", ratio=8e-3, fro=3e-3)
+    assert_close(one_a, two_a.cpu(), "merged CFG loop vs two-call loop, audio latents", ratio=8e-3, fro=3e-3)
+
+
 def test_step_at_mova_widths_vs_oracle():
     """MOVA widths (video 5120/40 heads, audio 1536/12, text 4096, freq 256, in 36 / out 16, audio 128 / 128) at one
     layer per tower and a short clip the CPU oracle finishes in seconds."""

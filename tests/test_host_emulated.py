@@ -207,9 +207,10 @@ def test_unsupported_step_options_fail_loudly(emu, step_case):
         B.WanModel(dim=256, in_dim=36, ffn_dim=512, out_dim=16, text_dim=64, freq_dim=256, eps=1e-6,
                    patch_size=(1, 2, 2), num_heads=2, num_layers=1, has_image_input=True)
     vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
-    with pytest.raises(NotImplementedError):  # batch of 2 latents
+    with pytest.raises(ValueError):  # three prompts against two latents: not a broadcastable batch
         pipe.inference_single_step(visual_dit=vis, visual_latents=inp["visual_latents"].repeat(2, 1, 1, 1, 1),
-                                   audio_latents=inp["audio_latents"], context=inp["context"].to(torch.bfloat16),
+                                   audio_latents=inp["audio_latents"],
+                                   context=inp["context"].to(torch.bfloat16).repeat(3, 1, 1),
                                    timestep=inp["timestep"], audio_timestep=None, video_fps=24.0)
     with pytest.raises(NotImplementedError):  # per-token time embedding
         vis.head(torch.zeros(1, 4, 256, dtype=torch.bfloat16), torch.zeros(1, 4, 256, dtype=torch.bfloat16))
@@ -373,6 +374,56 @@ def test_end_of_schedule_latents_host_logic(emu, step_case):
     n_blocks = cfg["visual_layers"] + cfg["audio_layers"]
     per_forward = 17 * n_blocks + 14 * min(cfg["visual_layers"], cfg["audio_layers"])
     assert emu["linear"] + emu["layernorm"] + emu["rmsnorm_rope_"] + emu["attention"] + emu["add_to_f32"] < 8 * (per_forward + 12)
+
+
+def test_cfg_merged_step_equals_two_calls(emu, step_case):
+    """SURVEY 8(f)2 / the reference's `cfg_merge` branch (pipeline_mova.py:443-445): [positive, negative] prompts as ONE
+    B = 2 forward.  No arithmetic couples the samples, so each half must equal its own B = 1 call -- exactly in this
+    emulation -- whether the latents are given once or per sample; and the merged denoising loop must end on the same
+    latents as the two-call loop."""
+    from dualforce_b200 import step
+
+    cfg, Pv, Pa, Pb, inp, gold, _ = step_case
+    vis, aud, bridge, pipe = build_step_towers(cfg, Pv, Pa, Pb, device="cpu")
+    g = torch.Generator().manual_seed(5)
+    pos = inp["context"].to(torch.bfloat16)
+    neg = (torch.randn(pos.shape, generator=g) * 0.5).to(torch.bfloat16)
+    kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"], audio_latents=inp["audio_latents"],
+              timestep=inp["timestep"], audio_timestep=None, video_fps=cfg["video_fps"])
+    pv, pa = pipe.inference_single_step(context=pos, **kw)
+    nv, na = pipe.inference_single_step(context=neg, **kw)
+    both = torch.cat([pos, neg], dim=0)
+    bv, ba = pipe.inference_single_step(context=both, **kw)
+    emu.clear()
+    pipe.inference_single_step(context=both, **kw)  # prompt memos warm, like the single call counted below
+    merged_calls = dict(emu)
+    assert bv.shape == (2,) + tuple(pv.shape[1:]) and ba.shape == (2,) + tuple(pa.shape[1:])
+    assert torch.equal(bv[0:1], pv) and torch.equal(bv[1:2], nv) and torch.equal(ba[0:1], pa) and torch.equal(ba[1:2], na)
+    # per-sample latents (what the reference's chunk(2) contract implies) give the same result
+    bv2, ba2 = pipe.inference_single_step(context=torch.cat([pos, neg], dim=0),
+                                          **dict(kw, visual_latents=inp["visual_latents"].repeat(2, 1, 1, 1, 1),
+                                                 audio_latents=inp["audio_latents"].repeat(2, 1, 1)))
+    assert torch.equal(bv2, bv) and torch.equal(ba2, ba)
+    # the batch really is batched: one GEMM / LayerNorm / attention launch per site, not one per sample
+    emu.clear()
+    pipe.inference_single_step(context=pos, **kw)
+    single_calls = dict(emu)
+    for name in ("linear", "layernorm", "attention"):
+        assert merged_calls[name] == single_calls[name], (name, merged_calls[name], single_calls[name])
+    # the loop of MOVA.__call__ with cfg_merge: same final latents as two calls per iteration
+    f, h, w = cfg["grid_size"]
+    latents = torch.randn(1, 16, f, 2 * h, 2 * w, generator=g)
+    condition = torch.randn(1, 20, f, 2 * h, 2 * w, generator=g)
+    audio = torch.randn(1, cfg["audio_in_dim"], cfg["audio_len"], generator=g)
+    sched = O.PairScheduler(num_inference_steps=3)
+    args = (pipe, latents, condition, audio, pos, neg, sched.get_pairs(), sched.timestep_to_sigma, cfg["video_fps"])
+    two_v, two_a = step.denoising_loop(*args, cfg_scale=5.0)
+    one_v, one_a = step.denoising_loop(*args, cfg_scale=5.0, cfg_merge=True)
+    assert torch.equal(two_v, one_v) and torch.equal(two_a, one_a)
+    # context parallelism keeps the two-call form
+    with pytest.raises(NotImplementedError):
+        pipe.forward_dual_tower_dit(vis, torch.zeros(2, 4, 256, dtype=torch.bfloat16), None, None, None, None, None,
+                                    torch.zeros(4, 64, dtype=torch.complex64), None, (1, 2, 2), 24.0, cp_mesh=object())
 
 
 def test_split_kv_bridge_attention_host_logic(emu):
