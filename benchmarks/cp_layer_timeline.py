@@ -31,7 +31,7 @@ def main():
                     help="exchange:set_sizes, e.g. peer:1,3,1  nccl:1,1,1,1,1  (sets only matter for an odd head count)")
     args = ap.parse_args()
     import bench
-    from dualforce_b200 import pipeline as pl
+    from dualforce_b200 import _lib, pipeline as pl
     from torch.distributed.device_mesh import init_device_mesh
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -52,9 +52,13 @@ def main():
     for policy in args.policies:
         if policy != "default":
             exch, _, sizes = policy.partition(":")
+            kernel_flags = exch == "peerk"  # peer windows with the kernel-based flag store / wait instead of memops
+            exch = "peer" if kernel_flags else exch
             pl.CPRuntime.exchange = exch
             for rt in pl._RUNTIMES.values():
                 rt.exchange = exch
+                if rt._px:
+                    rt._px.window.memops = (not kernel_flags) and bool(_lib.load().mova_b200_peer_memops_supported())
             pl.CPRuntime.set_sizes = tuple(int(v) for v in sizes.split(",")) if sizes else None
         for _ in range(2):
             pipe.inference_single_step(**kw)
@@ -83,7 +87,8 @@ def main():
             d[0] += a.elapsed_time(b)
             d[1] += 1
         if rank == 0:
-            used = sorted({("peer" if (rt._px and rt.exchange == "peer") else "nccl") for rt in pl._RUNTIMES.values()})
+            used = sorted({(("peer/memops" if rt._px.window.memops else "peer/kernel-flags")
+                            if (rt._px and rt.exchange == "peer") else "nccl") for rt in pl._RUNTIMES.values()})
             out = {"cp": world, "policy": policy, "exchange_used": used, "single_stream": bool(args.single_stream),
                    "forward_ms_plain": float(plain.item()), "forward_ms": e0.elapsed_time(e1),
                    "segments": {k: {"total_ms": round(v[0], 3), "count": v[1], "mean_ms": round(v[0] / v[1], 4)}

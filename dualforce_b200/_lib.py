@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmova_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> (restype, argtypes); mirrors include/mova_b200.h one to one
 SIGNATURES = {
@@ -67,8 +67,9 @@ SIGNATURES = {
     "mova_b200_peer_open": (c_int, [c_void_p, c_void_p]),
     "mova_b200_peer_close": (c_int, [c_void_p]),
     "mova_b200_peer_free": (c_int, [c_void_p]),
-    "mova_b200_peer_push": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
-    "mova_b200_peer_wait": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "mova_b200_peer_memops_supported": (c_int, []),
+    "mova_b200_peer_push": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mova_b200_peer_wait": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
 }
 
 EPI_BIAS, EPI_GELU_TANH, EPI_RESIDUAL = 0, 1, 2
@@ -113,9 +114,9 @@ LAUNCHES = 0  # kernel launches issued through the C ABI (each entry point enque
 _TIMERS = None  # bench.py sets this to a list; ops.attention then appends (start_event, end_event, B, Sq, Skv, H, D)
 
 
-def check(rc: int, what: str) -> None:
+def check(rc: int, what: str, launches: int = 1) -> None:
     global LAUNCHES
-    LAUNCHES += 1
+    LAUNCHES += launches
     if rc != 0:
         raise MovaB200Error(f"{what} failed (code {rc}): {last_error()}")
 

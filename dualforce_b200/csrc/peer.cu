@@ -11,10 +11,17 @@
 // Here every rank owns one receive window (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by its peers); the
 // per-(group, peer) chunks the GEMM already wrote destination-rank-major are contiguous, so the exchange is
 //     n x cudaMemcpyAsync(peer window + offset, chunk)      -- copy engines over NVLink, no SM, no kernel
-//     one 32-thread kernel that stores the epoch into a flag word in each destination's window (release, system scope)
-// and the consumer's stream runs one small kernel that polls its own flag words (acquire, system scope) before the
-// attention / o-projection launch.  The flag wait gives up with a trap after `timeout_ms` so a lost peer is an error
-// on this rank, never a hung GPU.
+//     the epoch into a flag word in each destination's window
+// and the consumer's stream waits for its own flag words before the attention / o-projection launch.
+//
+// Two implementations of the flag side, selected per call:
+//   * stream memory operations (default): cuStreamWriteValue64 puts the epoch into a word of this rank's window, n
+//     8-byte copy-engine copies carry it to the peers' flag words (stream order keeps them behind the data), and the
+//     consumer waits with cuStreamBatchMemOp(WAIT_VALUE_64 >=).  No kernel anywhere: measured on two B200s with the
+//     kernel version below, the 32-thread signal kernel queued behind the attention kernel (which owns every SM's
+//     registers and shared memory) and reached the peer 7 ms late (profiles/r02_timeline_cp2_peer_kernel_flags.json);
+//   * kernels (fallback / diagnostics): one 32-thread kernel stores the flags (st.release.sys), one polling kernel waits
+//     (ld.acquire.sys) and traps after `timeout_ms`, so a lost peer is an error on this rank instead of a silent wait.
 #include <stdint.h>
 #include <string.h>
 
@@ -67,9 +74,43 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int n, unsigne
   __threadfence_system();
 }
 
+struct MemOps {
+  PFN_cuStreamWriteValue64_v11070 write = nullptr;
+  PFN_cuStreamBatchMemOp_v11070 batch = nullptr;
+  bool tried = false;
+};
+
+static MemOps* memops() {
+  static MemOps m;
+  if (!m.tried) {
+    m.tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      m.write = reinterpret_cast<PFN_cuStreamWriteValue64_v11070>(p);
+    p = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamBatchMemOp", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      m.batch = reinterpret_cast<PFN_cuStreamBatchMemOp_v11070>(p);
+  }
+  return (m.write != nullptr && m.batch != nullptr) ? &m : nullptr;
+}
+
+static bool memops_supported() {
+  if (memops() == nullptr) return false;
+  int dev = 0, can64 = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  // cudaDevAttrReserved122 == CU_DEVICE_ATTRIBUTE_CAN_USE_64_BIT_STREAM_MEM_OPS
+  if (cudaDeviceGetAttribute(&can64, static_cast<cudaDeviceAttr>(122), dev) != cudaSuccess) return false;
+  return can64 != 0;
+}
+
 }  // namespace mv
 
 extern "C" {
+
+int mova_b200_peer_memops_supported(void) { return mv::memops_supported() ? 1 : 0; }
 
 int mova_b200_peer_alloc(int64_t nbytes, void** ptr, void* handle64) {
   MV_REQUIRE(nbytes > 0 && ptr != nullptr && handle64 != nullptr, "peer_alloc: bad arguments");
@@ -111,7 +152,7 @@ int mova_b200_peer_free(void* ptr) {
 }
 
 int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, const int64_t* nbytes, int n_flags,
-                        void* const* flags, int64_t epoch, void* stream) {
+                        void* const* flags, int64_t epoch, void* epoch_src, void* stream) {
   MV_REQUIRE(n_copies >= 0 && n_flags >= 0 && n_flags <= mv::PEER_MAX_FLAGS, "peer_push: %d copies / %d flags (max %d)",
              n_copies, n_flags, mv::PEER_MAX_FLAGS);
   MV_REQUIRE(epoch > 0, "peer_push: epoch must be positive");
@@ -120,22 +161,53 @@ int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, 
     if (nbytes[i] <= 0) continue;
     MV_CHECK_CUDA(cudaMemcpyAsync(dst[i], src[i], static_cast<size_t>(nbytes[i]), cudaMemcpyDefault, s));
   }
-  if (n_flags > 0) {
-    mv::PeerFlagList fl;
-    for (int i = 0; i < n_flags; ++i) {
-      MV_REQUIRE((reinterpret_cast<uintptr_t>(flags[i]) & 7) == 0, "peer_push: flag %d is not 8-byte aligned", i);
-      fl.p[i] = static_cast<unsigned long long*>(flags[i]);
-    }
-    mv::peer_signal_kernel<<<1, 32, 0, s>>>(fl, n_flags, static_cast<unsigned long long>(epoch));
-    MV_CHECK_CUDA(cudaGetLastError());
+  if (n_flags == 0) return 0;
+  for (int i = 0; i < n_flags; ++i)
+    MV_REQUIRE((reinterpret_cast<uintptr_t>(flags[i]) & 7) == 0, "peer_push: flag %d is not 8-byte aligned", i);
+  if (epoch_src != nullptr) {
+    // no kernel: the epoch goes into a word of this rank's window, copy-engine copies carry it to the flag words
+    mv::MemOps* m = mv::memops();
+    MV_REQUIRE(m != nullptr, "peer_push: stream memory operations are not available in this driver");
+    MV_REQUIRE((reinterpret_cast<uintptr_t>(epoch_src) & 7) == 0, "peer_push: epoch_src is not 8-byte aligned");
+    CUresult r = m->write(reinterpret_cast<CUstream>(s), reinterpret_cast<CUdeviceptr>(epoch_src),
+                          static_cast<cuuint64_t>(epoch), CU_STREAM_WRITE_VALUE_DEFAULT);
+    MV_REQUIRE(r == CUDA_SUCCESS, "peer_push: cuStreamWriteValue64 failed (CUresult %d)", static_cast<int>(r));
+    for (int i = 0; i < n_flags; ++i)
+      MV_CHECK_CUDA(cudaMemcpyAsync(flags[i], epoch_src, 8, cudaMemcpyDefault, s));
+    return 0;
   }
+  mv::PeerFlagList fl;
+  for (int i = 0; i < n_flags; ++i) fl.p[i] = static_cast<unsigned long long*>(flags[i]);
+  mv::peer_signal_kernel<<<1, 32, 0, s>>>(fl, n_flags, static_cast<unsigned long long>(epoch));
+  MV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int mova_b200_peer_wait(const void* flags, int n_flags, int64_t epoch, int timeout_ms, void* stream) {
+int mova_b200_peer_wait(const void* flags, int n_flags, int64_t epoch, int timeout_ms, int use_memops, void* stream) {
   MV_REQUIRE(flags != nullptr && n_flags > 0 && n_flags <= 1024, "peer_wait: bad flag range (%d)", n_flags);
   MV_REQUIRE((reinterpret_cast<uintptr_t>(flags) & 7) == 0, "peer_wait: flags are not 8-byte aligned");
   MV_REQUIRE(epoch > 0 && timeout_ms > 0, "peer_wait: epoch and timeout must be positive");
+  if (use_memops) {
+    mv::MemOps* m = mv::memops();
+    MV_REQUIRE(m != nullptr, "peer_wait: stream memory operations are not available in this driver");
+    CUstreamBatchMemOpParams ops[64];
+    int done = 0;
+    while (done < n_flags) {
+      const int n = (n_flags - done) < 64 ? (n_flags - done) : 64;
+      for (int i = 0; i < n; ++i) {
+        memset(&ops[i], 0, sizeof(ops[i]));
+        ops[i].waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_64;
+        ops[i].waitValue.address =
+            reinterpret_cast<CUdeviceptr>(static_cast<const unsigned long long*>(flags) + done + i);
+        ops[i].waitValue.value64 = static_cast<cuuint64_t>(epoch);
+        ops[i].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;
+      }
+      CUresult r = m->batch(reinterpret_cast<CUstream>(stream), static_cast<unsigned>(n), ops, 0);
+      MV_REQUIRE(r == CUDA_SUCCESS, "peer_wait: cuStreamBatchMemOp failed (CUresult %d)", static_cast<int>(r));
+      done += n;
+    }
+    return 0;
+  }
   uint32_t* dbg = nullptr;
   mv::debug_device_pointer(&dbg);
   const int threads = ((n_flags + 31) / 32) * 32;

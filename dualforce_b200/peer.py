@@ -38,6 +38,7 @@ __all__ = ["PeerExchange", "CudaIpcWindow", "PeerUnavailable"]
 FLAG_BYTES = 8192
 MAX_GROUPS = 32
 WAIT_TIMEOUT_MS = 120_000
+EPOCH_SRC_OFFSET = FLAG_BYTES - 64  # a word of the own window the epoch is staged in (stream memory-op signalling)
 
 
 class PeerUnavailable(RuntimeError):
@@ -59,12 +60,25 @@ class _RawCuda:
 
 
 class CudaIpcWindow:
-    """One cudaMalloc'd window per rank, mapped into every peer of ``group`` through CUDA IPC."""
+    """One cudaMalloc'd window per rank, mapped into every peer of ``group`` through CUDA IPC.
+
+    ``signal``: how flag words are written and awaited -- ``"memops"`` (stream memory operations + 8-byte copy-engine
+    copies: no kernel, so nothing queues behind an attention kernel that owns every SM) or ``"kernel"`` (a 32-thread
+    store kernel and a polling kernel with a time-out trap); ``None`` picks memops when the driver offers them."""
+
+    signal = None
 
     def __init__(self, group, rank: int, size: int, device: torch.device):
         from . import _lib
 
         self._lib = _lib
+        with torch.cuda.device(device):
+            supported = bool(_lib.load().mova_b200_peer_memops_supported())
+        if self.signal not in (None, "memops", "kernel"):
+            raise ValueError(f"CudaIpcWindow.signal must be None, 'memops' or 'kernel', got {self.signal!r}")
+        if self.signal == "memops" and not supported:
+            raise PeerUnavailable("stream memory operations requested but not supported by this driver / device")
+        self.memops = supported if self.signal is None else (self.signal == "memops")
         self.group, self.rank, self.size, self.device = group, rank, size, device
         self.capacity = 0
         self.local_ptr = 0
@@ -162,16 +176,17 @@ class CudaIpcWindow:
             dst[i], src[i], nb[i] = self.ptrs[r] + off, t.data_ptr(), nbytes
         fl = (ctypes.c_void_p * max(m, 1))()
         for i, (r, idx) in enumerate(flags):
-            assert 0 <= idx < FLAG_BYTES // 8
+            assert 0 <= idx < EPOCH_SRC_OFFSET // 8
             fl[i] = self.ptrs[r] + 8 * idx
-        rc = self._lib.load().mova_b200_peer_push(n, dst, src, nb, m, fl, int(epoch), _stream_ptr(stream))
-        self._lib.check(rc, "mova_b200_peer_push")
+        epoch_src = (self.local_ptr + EPOCH_SRC_OFFSET) if self.memops else None
+        rc = self._lib.load().mova_b200_peer_push(n, dst, src, nb, m, fl, int(epoch), epoch_src, _stream_ptr(stream))
+        self._lib.check(rc, "mova_b200_peer_push", launches=0 if self.memops else 1)
 
     def wait(self, first_flag: int, n_flags: int, epoch: int, stream=None) -> None:
-        assert 0 <= first_flag and first_flag + n_flags <= FLAG_BYTES // 8
+        assert 0 <= first_flag and first_flag + n_flags <= EPOCH_SRC_OFFSET // 8
         rc = self._lib.load().mova_b200_peer_wait(self.local_ptr + 8 * first_flag, n_flags, int(epoch), WAIT_TIMEOUT_MS,
-                                                  _stream_ptr(stream))
-        self._lib.check(rc, "mova_b200_peer_wait")
+                                                  1 if self.memops else 0, _stream_ptr(stream))
+        self._lib.check(rc, "mova_b200_peer_wait", launches=0 if self.memops else 1)
 
 
 class PeerExchange:
@@ -192,7 +207,7 @@ class PeerExchange:
         """Start one exchange round (one self-attention): returns this rank's ``recv [G, L, C]`` and
         ``back [G, cp, rows(me), w]`` views of its window.  ``C`` = 3 w for the fused q|k|v buffer."""
         cp = self.size
-        if G > MAX_GROUPS or 2 * MAX_GROUPS * cp * 8 > FLAG_BYTES:
+        if G > MAX_GROUPS or 2 * MAX_GROUPS * cp * 8 > EPOCH_SRC_OFFSET:
             raise ValueError(f"peer exchange: {G} head groups x {cp} ranks exceed the flag area")
         assert len(rows_per_rank) == cp and sum(rows_per_rank) == L
         item = torch.empty((), dtype=dtype).element_size()

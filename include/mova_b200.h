@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOVA_B200_ABI_VERSION 4
+#define MOVA_B200_ABI_VERSION 5
 
 /* epilogues of mova_b200_linear */
 #define MOVA_EPI_BIAS 0      /* C = A W^T + b                          nn.Linear                          */
@@ -203,22 +203,31 @@ int mova_b200_peer_open(const void* handle64, void** ptr);
 int mova_b200_peer_close(void* ptr);
 int mova_b200_peer_free(void* ptr);
 
-/*
- * Enqueue on `stream`: n_copies x cudaMemcpyAsync(dst[i], src[i], nbytes[i]) (local or peer-mapped device pointers,
- * contiguous chunks), then ONE kernel that stores `epoch` (> 0, increasing over the life of the windows) into each of
- * the n_flags (<= 32) 8-byte flag words -- typically one word in every destination's window -- with release semantics
- * at system scope.  A consumer that observes the flag observes the copied bytes.
- */
-int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, const int64_t* nbytes, int n_flags,
-                        void* const* flags, int64_t epoch, void* stream);
+/* 1 when the driver offers 64-bit stream memory operations (cuStreamWriteValue64 / cuStreamBatchMemOp) on the current device */
+int mova_b200_peer_memops_supported(void);
 
 /*
- * Enqueue on `stream` one kernel that returns once all n_flags consecutive 8-byte words at `flags` (this device's own
- * window) hold a value >= epoch (acquire, system scope).  After timeout_ms without progress it writes
- * {0x4d565057, flag index, epoch, value seen} to mova_b200_debug_record() and traps: a lost peer becomes a CUDA error
- * on this rank instead of a hung device.
+ * Enqueue on `stream`: n_copies x cudaMemcpyAsync(dst[i], src[i], nbytes[i]) (local or peer-mapped device pointers,
+ * contiguous chunks), then store `epoch` (> 0, increasing over the life of the windows) into each of the n_flags
+ * (<= 32) 8-byte flag words -- typically one word in every destination's window.  A consumer that observes the flag
+ * observes the copied bytes.
+ *   epoch_src != NULL  no kernel: cuStreamWriteValue64 puts the epoch into *epoch_src (a device word of the caller; all
+ *                      pushes sharing it must be queued on ONE stream), then one 8-byte copy per flag word carries it
+ *   epoch_src == NULL  one 32-thread kernel stores the flags (st.release.sys) -- needs an SM, so it queues behind a
+ *                      kernel that occupies the whole device
  */
-int mova_b200_peer_wait(const void* flags, int n_flags, int64_t epoch, int timeout_ms, void* stream);
+int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, const int64_t* nbytes, int n_flags,
+                        void* const* flags, int64_t epoch, void* epoch_src, void* stream);
+
+/*
+ * Enqueue on `stream` a wait until all n_flags consecutive 8-byte words at `flags` (this device's own window) hold a
+ * value >= epoch.
+ *   use_memops != 0  cuStreamBatchMemOp(WAIT_VALUE_64, GEQ): no kernel, no time-out
+ *   use_memops == 0  one polling kernel (ld.acquire.sys); after timeout_ms without progress it writes
+ *                    {0x4d565057, flag index, epoch, value seen} to mova_b200_debug_record() and traps: a lost peer
+ *                    becomes a CUDA error on this rank instead of a silent wait
+ */
+int mova_b200_peer_wait(const void* flags, int n_flags, int64_t epoch, int timeout_ms, int use_memops, void* stream);
 
 #ifdef __cplusplus
 }

@@ -85,7 +85,7 @@ def main():
     try:
         # both data paths of the Ulysses exchange: copy-engine pushes into peer windows + flag words (the default),
         # and NCCL all_to_all_single
-        for exchange in ("peer", "nccl"):
+        for exchange in (sys.argv[1:] or ["peer", "nccl"]):
             pl.CPRuntime.exchange = exchange
             pl._RUNTIMES.clear()
             mv, ma = run_check(rank, world)
