@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmova_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # name -> (restype, argtypes); mirrors include/mova_b200.h one to one
 SIGNATURES = {
@@ -68,7 +68,8 @@ SIGNATURES = {
     "mova_b200_peer_close": (c_int, [c_void_p]),
     "mova_b200_peer_free": (c_int, [c_void_p]),
     "mova_b200_peer_memops_supported": (c_int, []),
-    "mova_b200_peer_push": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mova_b200_peer_push": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p,
+                                    c_void_p]),
     "mova_b200_peer_wait": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
 }
 

@@ -152,7 +152,7 @@ int mova_b200_peer_free(void* ptr) {
 }
 
 int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, const int64_t* nbytes, int n_flags,
-                        void* const* flags, int64_t epoch, void* epoch_src, void* stream) {
+                        void* const* flags, int64_t local_mask, int64_t epoch, void* epoch_src, void* stream) {
   MV_REQUIRE(n_copies >= 0 && n_flags >= 0 && n_flags <= mv::PEER_MAX_FLAGS, "peer_push: %d copies / %d flags (max %d)",
              n_copies, n_flags, mv::PEER_MAX_FLAGS);
   MV_REQUIRE(epoch > 0, "peer_push: epoch must be positive");
@@ -172,8 +172,17 @@ int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, 
     CUresult r = m->write(reinterpret_cast<CUstream>(s), reinterpret_cast<CUdeviceptr>(epoch_src),
                           static_cast<cuuint64_t>(epoch), CU_STREAM_WRITE_VALUE_DEFAULT);
     MV_REQUIRE(r == CUDA_SUCCESS, "peer_push: cuStreamWriteValue64 failed (CUresult %d)", static_cast<int>(r));
-    for (int i = 0; i < n_flags; ++i)
-      MV_CHECK_CUDA(cudaMemcpyAsync(flags[i], epoch_src, 8, cudaMemcpyDefault, s));
+    for (int i = 0; i < n_flags; ++i) {
+      if ((local_mask >> i) & 1) {
+        // a word of this device's own memory: written by the stream front end (a same-device cudaMemcpyAsync runs on
+        // the SMs and would queue behind a kernel that owns them -- profiles/r02_ce_overlap_probe.json)
+        r = m->write(reinterpret_cast<CUstream>(s), reinterpret_cast<CUdeviceptr>(flags[i]),
+                     static_cast<cuuint64_t>(epoch), CU_STREAM_WRITE_VALUE_DEFAULT);
+        MV_REQUIRE(r == CUDA_SUCCESS, "peer_push: cuStreamWriteValue64 failed (CUresult %d)", static_cast<int>(r));
+      } else {
+        MV_CHECK_CUDA(cudaMemcpyAsync(flags[i], epoch_src, 8, cudaMemcpyDefault, s));
+      }
+    }
     return 0;
   }
   mv::PeerFlagList fl;

@@ -175,11 +175,15 @@ class CudaIpcWindow:
             assert off + nbytes <= self.capacity
             dst[i], src[i], nb[i] = self.ptrs[r] + off, t.data_ptr(), nbytes
         fl = (ctypes.c_void_p * max(m, 1))()
+        local_mask = 0
         for i, (r, idx) in enumerate(flags):
             assert 0 <= idx < EPOCH_SRC_OFFSET // 8
             fl[i] = self.ptrs[r] + 8 * idx
+            if r == self.rank:
+                local_mask |= 1 << i
         epoch_src = (self.local_ptr + EPOCH_SRC_OFFSET) if self.memops else None
-        rc = self._lib.load().mova_b200_peer_push(n, dst, src, nb, m, fl, int(epoch), epoch_src, _stream_ptr(stream))
+        rc = self._lib.load().mova_b200_peer_push(n, dst, src, nb, m, fl, local_mask, int(epoch), epoch_src,
+                                                  _stream_ptr(stream))
         self._lib.check(rc, "mova_b200_peer_push", launches=0 if self.memops else 1)
 
     def wait(self, first_flag: int, n_flags: int, epoch: int, stream=None) -> None:
@@ -224,29 +228,62 @@ class PeerExchange:
         back = self.window.local_tensor(self._back_off, (G, cp, self._rows[self.rank], w), dtype)
         return recv, back
 
+    # Remote and local chunks go separately.  Remote chunks are peer copies: copy engines, they run beside a kernel
+    # that owns every SM.  The chunk a rank keeps for itself is a same-device copy, which the driver may run on the
+    # SMs -- queued behind the attention kernel it would stall the stream it sits on (measured,
+    # profiles/r02_ce_overlap_probe.json), so local chunks are pushed where no attention kernel is in the way: all
+    # groups at once BEFORE the first remote push (inbound), and on the compute stream after the last attention set
+    # (outbound).
+    def _order(self):
+        cp, me = self.size, self.rank
+        return [(me + 1 + i) % cp for i in range(cp - 1)]  # every rank starts with a different peer
+
     def push_in(self, g: int, send_g: torch.Tensor, stream=None) -> None:
-        """``send_g [cp, rows(me), C]``: chunk d goes to rank d's ``recv[g, rows_before(me):, :]``."""
+        """``send_g [cp, rows(me), C]``: chunk d (d != me) goes to rank d's ``recv[g, rows_before(me):, :]``."""
         cp, me = self.size, self.rank
         assert tuple(send_g.shape) == (cp, self._rows[me], self._C)
+        order = self._order()
+        if not order:
+            return
         off = self._recv_off + (g * self._L + self._row_off[me]) * self._C * self._item
-        order = [(me + 1 + i) % cp for i in range(cp)]  # remote chunks first, every rank starts with another peer
         self.window.push([(d, off, send_g[d]) for d in order],
                          [(d, self.flag_index(0, g, me, cp)) for d in order], self.epoch, stream)
+
+    def push_in_local(self, send: torch.Tensor, stream=None) -> None:
+        """``send [G, cp, rows(me), C]``: this rank's own chunk of every group into its own ``recv``."""
+        cp, me, G = self.size, self.rank, self._G
+        assert tuple(send.shape) == (G, cp, self._rows[me], self._C)
+        copies = [(me, self._recv_off + (g * self._L + self._row_off[me]) * self._C * self._item, send[g, me])
+                  for g in range(G)]
+        self.window.push(copies, [(me, self.flag_index(0, g, me, cp)) for g in range(G)], self.epoch, stream)
 
     def wait_in(self, g_first: int, g_last: int, stream=None) -> None:
         cp = self.size
         self.window.wait(self.flag_index(0, g_first, 0, cp), (g_last - g_first + 1) * cp, self.epoch, stream)
 
     def push_out(self, g: int, o: torch.Tensor, stream=None) -> None:
-        """``o [L, w]`` (all tokens, my heads of group g): rows of rank d go to rank d's ``back[g, me]``."""
+        """``o [L, w]`` (all tokens, my heads of group g): rows of rank d (d != me) go to rank d's ``back[g, me]``."""
         cp, me = self.size, self.rank
         assert tuple(o.shape) == (self._L, self._w) and o.is_contiguous()
-        order = [(me + 1 + i) % cp for i in range(cp)]
+        order = self._order()
+        if not order:
+            return
         copies = []
         for d in order:
             off = self._back_off + (g * cp + me) * self._rows[d] * self._w * self._item
             copies.append((d, off, o[self._row_off[d]:self._row_off[d] + self._rows[d]]))
         self.window.push(copies, [(d, self.flag_index(1, g, me, cp)) for d in order], self.epoch, stream)
+
+    def push_out_local(self, outs: Sequence[Tuple[int, torch.Tensor]], stream=None) -> None:
+        """``outs``: (group g, ``o [L, w]``) for every group: this rank's own rows into its own ``back[g, me]``."""
+        cp, me = self.size, self.rank
+        lo, n = self._row_off[me], self._rows[me]
+        copies, flags = [], []
+        for g, o in outs:
+            assert tuple(o.shape) == (self._L, self._w) and o.is_contiguous()
+            copies.append((me, self._back_off + (g * cp + me) * n * self._w * self._item, o[lo:lo + n]))
+            flags.append((me, self.flag_index(1, g, me, cp)))
+        self.window.push(copies, flags, self.epoch, stream)
 
     def wait_out(self, stream=None) -> None:
         cp = self.size

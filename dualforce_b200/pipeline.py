@@ -182,6 +182,8 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
     in_done = []
     with on_comm():
         wait(comm, ready)
+        if px is not None:
+            px.push_in_local(send, stream=comm)  # same-device copies first: nothing on the SMs is in their way yet
         for g in range(G):
             with _seg(f"all_to_all_in[{g}]", "comm"):
                 if px is not None:
@@ -223,6 +225,7 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
         for ev in out_done:
             wait(main, ev)
         if px is not None:
+            px.push_out_local([(g, o[i]) for gs, o in zip(sets, outs) for i, g in enumerate(gs)], stream=main)
             px.wait_out(stream=main)
     with _seg("o_proj"):
         return ops.linear(back.view(G * cp, Lc, wd), wo, sa.o.bias, epilogue=ops.EPI_RESIDUAL, residual=x[0], gate=gate,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOVA_B200_ABI_VERSION 5
+#define MOVA_B200_ABI_VERSION 6
 
 /* epilogues of mova_b200_linear */
 #define MOVA_EPI_BIAS 0      /* C = A W^T + b                          nn.Linear                          */
@@ -212,12 +212,14 @@ int mova_b200_peer_memops_supported(void);
  * (<= 32) 8-byte flag words -- typically one word in every destination's window.  A consumer that observes the flag
  * observes the copied bytes.
  *   epoch_src != NULL  no kernel: cuStreamWriteValue64 puts the epoch into *epoch_src (a device word of the caller; all
- *                      pushes sharing it must be queued on ONE stream), then one 8-byte copy per flag word carries it
+ *                      pushes sharing it must be queued on ONE stream), then one 8-byte peer copy per flag word carries
+ *                      it; flag i with bit i of local_mask set lives in THIS device's memory and is written directly
+ *                      with cuStreamWriteValue64 (a same-device copy would run on the SMs)
  *   epoch_src == NULL  one 32-thread kernel stores the flags (st.release.sys) -- needs an SM, so it queues behind a
  *                      kernel that occupies the whole device
  */
 int mova_b200_peer_push(int n_copies, void* const* dst, const void* const* src, const int64_t* nbytes, int n_flags,
-                        void* const* flags, int64_t epoch, void* epoch_src, void* stream);
+                        void* const* flags, int64_t local_mask, int64_t epoch, void* epoch_src, void* stream);
 
 /*
  * Enqueue on `stream` a wait until all n_flags consecutive 8-byte words at `flags` (this device's own window) hold a
