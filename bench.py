@@ -320,6 +320,8 @@ def run_b200_arm(args):
     _pl.CPRuntime.exchange = args.cp_exchange
     if args.cp_sets:
         _pl.CPRuntime.set_sizes = tuple(int(v) for v in args.cp_sets.split(","))
+    if args.cp_push_streams:
+        _pl.CPRuntime.push_streams_n = args.cp_push_streams
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
         from torch.distributed.device_mesh import init_device_mesh
@@ -541,6 +543,7 @@ def run_b200_arm(args):
                        "cp_audio_side_stream": (not args.cp_single_stream) if world > 1 else None,
                        "cp_exchange": cp_exchange_used(_pl) if world > 1 else None,
                        "cp_attention_sets": args.cp_sets or "default",
+                       "cp_push_streams": _pl.CPRuntime.push_streams_n if world > 1 else None,
                        "cfg_form": "merged: one B=2 forward per step" if args.cfg_merge else "two B=1 forwards per step",
                        "video_experts_resident": experts,
                        "launch_mode": "cuda graph replay" if use_graph else "eager",
@@ -676,6 +679,8 @@ def main():
     ap.add_argument("--cp-exchange", choices=["peer", "nccl"], default="peer",
                     help="Ulysses exchange data path: copy-engine pushes into peer windows + flags (default), or NCCL "
                          "all_to_all_single (round-1 path)")
+    ap.add_argument("--cp-push-streams", type=int, default=0,
+                    help="A/B: streams the remote pushes of the peer exchange are dealt over (default: the build's)")
     ap.add_argument("--cp-sets", default="", help="A/B: attention set sizes for an odd head count per rank, e.g. 1,3,1")
     ap.add_argument("--experts", type=int, default=None, help="resident video experts (default 2, as in the reference)")
     ap.add_argument("--schedule", type=int, default=0,

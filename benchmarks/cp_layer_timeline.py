@@ -52,6 +52,10 @@ def main():
     for policy in args.policies:
         if policy != "default":
             exch, _, sizes = policy.partition(":")
+            exch, _, nstreams = exch.partition("@")  # peer@4 = remote pushes dealt over 4 streams
+            pl.CPRuntime.push_streams_n = int(nstreams) if nstreams else 1
+            for rt in pl._RUNTIMES.values():
+                rt.push_streams_n = pl.CPRuntime.push_streams_n
             kernel_flags = exch == "peerk"  # peer windows with the kernel-based flag store / wait instead of memops
             exch = "peer" if kernel_flags else exch
             pl.CPRuntime.exchange = exch

@@ -38,7 +38,8 @@ __all__ = ["PeerExchange", "CudaIpcWindow", "PeerUnavailable"]
 FLAG_BYTES = 8192
 MAX_GROUPS = 32
 WAIT_TIMEOUT_MS = 120_000
-EPOCH_SRC_OFFSET = FLAG_BYTES - 64  # a word of the own window the epoch is staged in (stream memory-op signalling)
+EPOCH_SRC_SLOTS = 8
+EPOCH_SRC_OFFSET = FLAG_BYTES - 8 * EPOCH_SRC_SLOTS  # words of the own window the epoch is staged in (memop signalling)
 
 
 class PeerUnavailable(RuntimeError):
@@ -57,6 +58,20 @@ class _RawCuda:
     def __init__(self, ptr: int, nbytes: int):
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
                                          "version": 2, "strides": None}
+
+
+def deal_by_destination(copies, flags, k: int):
+    """Split one push into at most ``k`` pushes, destinations dealt round-robin in order of first appearance; every
+    destination's copies and flag stay together and in order.  Returns ``[(copies_j, flags_j), ...]`` (non-empty)."""
+    dests = []
+    for r in [c[0] for c in copies] + [f[0] for f in flags]:
+        if r not in dests:
+            dests.append(r)
+    out = []
+    for j in range(min(k, len(dests))):
+        mine = set(dests[j::k])
+        out.append(([c for c in copies if c[0] in mine], [f for f in flags if f[0] in mine]))
+    return out
 
 
 class CudaIpcWindow:
@@ -164,7 +179,20 @@ class CudaIpcWindow:
     def push(self, copies: Sequence[Tuple[int, int, torch.Tensor]], flags: Sequence[Tuple[int, int]], epoch: int,
              stream=None) -> None:
         """``copies``: (destination rank, byte offset in its window, contiguous source tensor on this device);
-        ``flags``: (destination rank, flag index) stored with ``epoch`` after all copies."""
+        ``flags``: (destination rank, flag index) stored with ``epoch`` after the copies.
+
+        ``stream`` may be a list of streams: the destinations are then dealt round-robin over them (a destination's
+        copies and its flag stay on one stream, in order), so the ~9 us a copy-engine operation costs on a stream are
+        paid in parallel.  The caller orders the streams against producers and consumers with events."""
+        if isinstance(stream, (list, tuple)) and len(stream) > 1:
+            for j, (cj, fj) in enumerate(deal_by_destination(copies, flags, len(stream))):
+                self._push_one(cj, fj, epoch, stream[j], j)
+            return
+        if isinstance(stream, (list, tuple)):
+            stream = stream[0] if stream else None
+        self._push_one(copies, flags, epoch, stream, 0)
+
+    def _push_one(self, copies, flags, epoch: int, stream, slot: int) -> None:
         n, m = len(copies), len(flags)
         dst = (ctypes.c_void_p * max(n, 1))()
         src = (ctypes.c_void_p * max(n, 1))()
@@ -181,7 +209,8 @@ class CudaIpcWindow:
             fl[i] = self.ptrs[r] + 8 * idx
             if r == self.rank:
                 local_mask |= 1 << i
-        epoch_src = (self.local_ptr + EPOCH_SRC_OFFSET) if self.memops else None
+        assert 0 <= slot < EPOCH_SRC_SLOTS  # one staging word per push stream: their epochs may differ in flight
+        epoch_src = (self.local_ptr + EPOCH_SRC_OFFSET + 8 * slot) if self.memops else None
         rc = self._lib.load().mova_b200_peer_push(n, dst, src, nb, m, fl, local_mask, int(epoch), epoch_src,
                                                   _stream_ptr(stream))
         self._lib.check(rc, "mova_b200_peer_push", launches=0 if self.memops else 1)

@@ -38,6 +38,9 @@ class CPRuntime:
     # Attention sets when the heads per rank do not split in two groups (cp = 8: 5 heads), see cp.head_group_sets;
     # None = (1, n - 2, 1) with the peer exchange, one set per head with NCCL.
     set_sizes = None
+    # Streams the remote pushes of the peer exchange are dealt over (by destination): a copy-engine operation costs
+    # ~9 us on its stream, 14 of them make one head group's exchange at cp = 8.
+    push_streams_n = 1
 
     def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: Optional[int] = None):
         self.group, self.rank, self.size, self.device = group, rank, size, device
@@ -51,6 +54,14 @@ class CPRuntime:
         # more than two attention sets per layer (odd head count per rank): launches alternate between these
         self.attn_streams = [torch.cuda.Stream(device=device) for _ in range(2)] if cuda else []
         self._px = None  # PeerExchange, False once it proved unavailable (tests inject a shared-memory one)
+        self._push_streams = [self.comm_stream] if cuda else []
+
+    def push_streams(self):
+        """The communication stream plus ``push_streams_n - 1`` more (created on first use, capped at 8)."""
+        n = max(1, min(int(self.push_streams_n), 8, max(self.size - 1, 1)))
+        while self.device.type == "cuda" and len(self._push_streams) < n:
+            self._push_streams.append(torch.cuda.Stream(device=self.device))
+        return self._push_streams[:n]
 
     def peer_exchange(self):
         """The peer-memory exchange for this runtime, or None (NCCL path).  First use is collective."""
@@ -180,14 +191,17 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
         back = torch.empty(G, cp, Lc, wd, dtype=torch.bfloat16, device=h.device)
     outs = [torch.empty(len(gs), L, wd, dtype=torch.bfloat16, device=h.device) for gs in sets]
     in_done = []
+    pushers = rt.push_streams() if (px is not None and comm is not None) else None  # pushers[0] is `comm`
     with on_comm():
         wait(comm, ready)
         if px is not None:
+            for ps in (pushers or [])[1:]:
+                wait(ps, ready)
             px.push_in_local(send, stream=comm)  # same-device copies first: nothing on the SMs is in their way yet
         for g in range(G):
             with _seg(f"all_to_all_in[{g}]", "comm"):
                 if px is not None:
-                    px.push_in(g, send[g], stream=comm)
+                    px.push_in(g, send[g], stream=pushers if pushers else comm)
                 else:
                     cpmod.scatter_heads(send[g], rows_per_rank, rt.rank, rt.group, out=recv[g])  # [L, 3*wd]
             in_done.append(record(comm))
@@ -214,13 +228,17 @@ def _self_attention_cp(block: DiTBlock, h: torch.Tensor, tables, x: torch.Tensor
             att = record(st)
         with on_comm():
             wait(comm, att)
+            for ps in (pushers or [])[1:]:
+                wait(ps, att)
             with _seg(f"all_to_all_out{gs}", "comm"):
                 for i, g in enumerate(gs):
                     if px is not None:
-                        px.push_out(g, o[i], stream=comm)
+                        px.push_out(g, o[i], stream=pushers if pushers else comm)
                     else:
                         cpmod.gather_heads(o[i], rows_per_rank, rt.rank, rt.group, out=back[g])
             out_done.append(record(comm))
+    for ps in (pushers or [])[1:]:  # the other push streams: one event after their last push covers all of them
+        out_done.append(record(ps))
     with _seg("wait_all_to_all_out"):
         for ev in out_done:
             wait(main, ev)

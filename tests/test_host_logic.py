@@ -202,3 +202,27 @@ def test_activation_hook_installs_on_first_call(monkeypatch):
     monkeypatch.setenv("MOVA_B200_CUDA_GRAPH", "1")
     other("c")
     assert calls[-2:] == [("install", True), ("call", "c", 1)]
+
+
+def test_peer_push_is_dealt_by_destination():
+    """dualforce_b200.peer: with k push streams every destination's copies and its flag stay on ONE stream, in order,
+    and nothing is lost or duplicated; flag indices of the exchange are disjoint per (direction, group, source)."""
+    from dualforce_b200 import peer
+
+    order = [3, 4, 5, 6, 7, 0, 1]  # rank 2 of 8: remote destinations in push order
+    copies = [(d, 100 * d, f"chunk{d}") for d in order]
+    flags = [(d, 17) for d in order]
+    for k in (1, 2, 3, 4, 7, 8):
+        parts = peer.deal_by_destination(copies, flags, k)
+        assert len(parts) == min(k, len(order))
+        seen = []
+        for cj, fj in parts:
+            assert [c[0] for c in cj] == [f[0] for f in fj]  # a destination's data and flag travel together
+            seen += [c[0] for c in cj]
+        assert sorted(seen) == sorted(order)
+        assert [c[0] for c in parts[0][0]] == order[0::k]
+    # local pushes (one destination, several groups) stay one push
+    local = peer.deal_by_destination([(2, g, None) for g in range(5)], [(2, g) for g in range(5)], 4)
+    assert len(local) == 1 and len(local[0][0]) == 5 and len(local[0][1]) == 5
+    idx = {peer.PeerExchange.flag_index(d, g, s, 8) for d in (0, 1) for g in range(peer.MAX_GROUPS) for s in range(8)}
+    assert len(idx) == 2 * peer.MAX_GROUPS * 8 and max(idx) < peer.EPOCH_SRC_OFFSET // 8
