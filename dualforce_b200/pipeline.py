@@ -39,8 +39,10 @@ class CPRuntime:
     # None = (1, n - 2, 1) with the peer exchange, one set per head with NCCL.
     set_sizes = None
     # Streams the remote pushes of the peer exchange are dealt over (by destination): a copy-engine operation costs
-    # ~9 us on its stream, 14 of them make one head group's exchange at cp = 8.
-    push_streams_n = 1
+    # ~9 us on its stream and 14 of them make one head group's exchange at cp = 8.  0 = one stream per peer (measured
+    # at cp = 8, profiles/r02_timeline_cp8_push_streams.json: 300.5 ms per forward against 302.1-304.5 with one stream,
+    # bench 1.655 against 1.623 steps/s).
+    push_streams_n = 0
 
     def __init__(self, group, rank: int, size: int, device: torch.device, head_groups: Optional[int] = None):
         self.group, self.rank, self.size, self.device = group, rank, size, device
@@ -58,7 +60,8 @@ class CPRuntime:
 
     def push_streams(self):
         """The communication stream plus ``push_streams_n - 1`` more (created on first use, capped at 8)."""
-        n = max(1, min(int(self.push_streams_n), 8, max(self.size - 1, 1)))
+        want = int(self.push_streams_n) or (self.size - 1)
+        n = max(1, min(want, 8, max(self.size - 1, 1)))
         while self.device.type == "cuda" and len(self._push_streams) < n:
             self._push_streams.append(torch.cuda.Stream(device=self.device))
         return self._push_streams[:n]
