@@ -543,7 +543,7 @@ def run_b200_arm(args):
                        "cp_audio_side_stream": (not args.cp_single_stream) if world > 1 else None,
                        "cp_exchange": cp_exchange_used(_pl) if world > 1 else None,
                        "cp_attention_sets": args.cp_sets or "default",
-                       "cp_push_streams": (_pl.CPRuntime.push_streams_n or "one per peer") if world > 1 else None,
+                       "cp_push_streams": (_pl.CPRuntime.push_streams_n or ("one per peer" if world >= 8 else 1)) if world > 1 else None,
                        "cfg_form": "merged: one B=2 forward per step" if args.cfg_merge else "two B=1 forwards per step",
                        "video_experts_resident": experts,
                        "launch_mode": "cuda graph replay" if use_graph else "eager",

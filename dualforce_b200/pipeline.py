@@ -39,7 +39,7 @@ class CPRuntime:
     # None = (1, n - 2, 1) with the peer exchange, one set per head with NCCL.
     set_sizes = None
     # Streams the remote pushes of the peer exchange are dealt over (by destination): a copy-engine operation costs
-    # ~9 us on its stream and 14 of them make one head group's exchange at cp = 8.  0 = one stream per peer (measured
+    # ~9 us on its stream and 14 of them make one head group's exchange at cp = 8.  0 = one stream per peer at cp >= 8 (measured
     # at cp = 8, profiles/r02_timeline_cp8_push_streams.json: 300.5 ms per forward against 302.1-304.5 with one stream,
     # bench 1.655 against 1.623 steps/s).
     push_streams_n = 0
@@ -60,7 +60,9 @@ class CPRuntime:
 
     def push_streams(self):
         """The communication stream plus ``push_streams_n - 1`` more (created on first use, capped at 8)."""
-        want = int(self.push_streams_n) or (self.size - 1)
+        # 0: one stream per peer where the exchange is latency-bound (many small chunks: measured at cp = 8); with 2 or
+        # 4 ranks the chunks are 60-165 MB each, a single stream already runs at NVLink bandwidth (measured at cp = 2)
+        want = int(self.push_streams_n) or (self.size - 1 if self.size >= 8 else 1)
         n = max(1, min(want, 8, max(self.size - 1, 1)))
         while self.device.type == "cuda" and len(self._push_streams) < n:
             self._push_streams.append(torch.cuda.Stream(device=self.device))
