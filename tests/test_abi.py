@@ -106,3 +106,26 @@ def test_ctypes_signatures_match_the_header_argument_by_argument():
         assert _lib.SIGNATURES[name][1] == want, f"{name}: header {params} vs ctypes {_lib.SIGNATURES[name][1]}"
         seen += 1
     assert seen == len(_lib.SIGNATURES)
+
+
+def test_peer_entry_points_validate_arguments_before_touching_the_device():
+    """csrc/peer.cu: bad arguments are rejected with a message (no CUDA call is made for them, so this runs on a
+    CPU-only box): too many flags per push, non-positive epochs, unaligned or missing flag words."""
+    import ctypes
+
+    from dualforce_b200 import _lib
+
+    lib = _lib.load()
+    none = ctypes.c_void_p()
+    arr = (ctypes.c_void_p * 1)()
+    nb = (ctypes.c_int64 * 1)()
+    assert lib.mova_b200_peer_push(0, arr, arr, nb, 33, arr, 0, 1, none, none) != 0
+    assert "flags" in _lib.last_error()
+    assert lib.mova_b200_peer_push(0, arr, arr, nb, 0, arr, 0, 0, none, none) != 0
+    assert "epoch" in _lib.last_error()
+    assert lib.mova_b200_peer_wait(none, 4, 1, 1000, 1, none) != 0
+    assert lib.mova_b200_peer_wait(ctypes.c_void_p(12), 4, 1, 1000, 1, none) != 0  # not 8-byte aligned
+    assert "aligned" in _lib.last_error()
+    assert lib.mova_b200_peer_wait(ctypes.c_void_p(16), 4, 0, 1000, 1, none) != 0
+    assert lib.mova_b200_peer_alloc(0, ctypes.byref(none), ctypes.create_string_buffer(64)) != 0
+    assert lib.mova_b200_peer_open(None, ctypes.byref(none)) != 0
