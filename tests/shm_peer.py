@@ -14,8 +14,13 @@ FLAG_WORDS = 1024
 
 
 class ShmWindow:
-    def __init__(self, rank: int, size: int, tag: str, group=None):
+    def __init__(self, rank: int, size: int, tag: str, group=None, jitter_ms: float = 0.0):
         self.rank, self.size, self.tag, self.group = rank, size, tag, group
+        # de-synchronise the ranks: a random pause before every push and wait.  The exchange sends no acknowledgements
+        # (dualforce_b200/peer.py relies on data dependencies), so a rank that runs ahead must never overwrite what a
+        # slower peer has not consumed yet
+        self.jitter_ms = jitter_ms
+        self._rng = np.random.default_rng(1234 + rank)
         self.capacity = 0
         self.maps = []
         self.generation = 0
@@ -58,7 +63,12 @@ class ShmWindow:
         assert offset % 16 == 0 and offset + n <= self.capacity
         return self._bytes(self.rank)[offset:offset + n].view(dtype).view(*shape)
 
+    def _pause(self):
+        if self.jitter_ms > 0:
+            time.sleep(float(self._rng.uniform(0, self.jitter_ms)) * 1e-3)
+
     def push(self, copies, flags, epoch, stream=None):
+        self._pause()
         for r, off, t in copies:
             assert t.is_contiguous()
             src = t.reshape(-1).view(torch.uint8)
@@ -70,6 +80,7 @@ class ShmWindow:
         self.pushes += 1
 
     def wait(self, first_flag, n_flags, epoch, stream=None):
+        self._pause()
         words = self.maps[self.rank][8 * first_flag:8 * (first_flag + n_flags)].view(np.uint64)
         t0 = time.time()
         while not bool((words >= np.uint64(epoch)).all()):

@@ -62,7 +62,7 @@ def _worker(rank, world, port, grid, heads, results, exchange="collective", set_
             from shm_peer import ShmWindow
 
             rt = pl.CPRuntime.from_mesh(mesh, torch.device("cpu"))
-            window = ShmWindow(rank, world, str(port))
+            window = ShmWindow(rank, world, str(port), jitter_ms=3.0 * (1 + rank))  # ranks drift apart on purpose
             rt._px = peer.PeerExchange(window, rank, world)
             pl.CPRuntime.set_sizes = set_sizes
         kw = dict(visual_dit=vis, visual_latents=inp["visual_latents"], audio_latents=inp["audio_latents"], context=ctx,
