@@ -32,6 +32,7 @@
 // warpgroups on the MUFU phase (938), two threads per query row / 16 softmax warps (1178: the phase lengths did not
 // move, i.e. they are set by shared units -- MUFU 16 lanes/clk, TMEM read port -- not by per-thread issue).
 // This kernel: 1271-1279 TFLOP/s at S = 43120, 40 heads.
+#include <atomic>
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -385,12 +386,12 @@ template <int EMU, bool TRACE>
 static int launch_attn(dim3 grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                        const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
   auto kernel = attn_fwd_kernel<EMU, TRACE>;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];  // zero-initialised; per-device "attribute set" latch, safe across host threads
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     MV_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   MV_CHECK_CUDA(cudaGetLastError());

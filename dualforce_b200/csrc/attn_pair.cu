@@ -33,6 +33,7 @@
 //     polynomial on the FMA pipe (MUFU relief);
 //   * epilogue: the two warpgroups take 64 output columns each: O / (l_A + l_B) -> bf16 -> swizzled smem (the dead Q
 //     tile) -> TMA store (rows >= Sq are clipped).
+#include <atomic>
 #include <stdlib.h>
 
 #include "attn_common.cuh"
@@ -476,12 +477,12 @@ static int launch_attn_pair_t(int B, int Sq, int H, cudaStream_t stream, const C
                               const CUtensorMap& tmV, const CUtensorMap& tmO, const AttnParams& p) {
   using Cfg = APCfg<CG, BN>;
   auto kernel = attn_pair_kernel<CG, BN, EMU, TRACE>;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];  // zero-initialised; per-device "attribute set" latch, safe across host threads
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     MV_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   const int tiles = (Sq + 127) / 128;
   cudaLaunchConfig_t cfg = {};

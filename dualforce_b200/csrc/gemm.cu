@@ -16,6 +16,7 @@
 //     stream past it once per panel; TMA loads of W carry the L2 evict_last hint, the C stores evict_first (ncu of the
 //     round-1 kernel: 8.3-9.3 GB of DRAM traffic per QKV GEMM against 1.9 GB algorithmic -- DRAM joules are clock on a
 //     power-capped part).
+#include <atomic>
 #include "common.cuh"
 #include "host_utils.h"
 #include "../../include/mova_b200.h"
@@ -304,12 +305,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   using Cfg = GemmCfg<CG>;
   auto kernel = gemm_bf16_kernel<CG, EPI>;
   debug_attach();
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];  // zero-initialised; per-device "attribute set" latch, safe across host threads
   int dev = 0;
   MV_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     MV_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   const int m_tiles = (p.M + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
