@@ -132,3 +132,66 @@ def test_usp_attention_processor_world2():
     results = mgr.dict()
     mp.spawn(_usp_worker, args=(2, _free_port(), results), nprocs=2, join=True)
     assert len(results) == 2 and all(e < 1e-5 for e in results.values()), dict(results)
+
+
+def _peer_exchange_worker(rank, world, port, results):
+    """dualforce_b200.peer.PeerExchange on its own (shared-memory windows): ragged rows, several head groups, a second
+    round with larger shapes that forces the windows to grow (collective re-allocation), flags by epoch."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dualforce_b200 import peer
+        from shm_peer import ShmWindow
+
+        win = ShmWindow(rank, world, f"px{port}", jitter_ms=2.0 * (1 + rank))
+        px = peer.PeerExchange(win, rank, world)
+        ok = True
+        for rnd, (G, rows, w) in enumerate([(2, [5, 3, 4][:world] if world == 3 else [5, 3][:world], 128),
+                                            (3, [70, 64, 61][:world] if world == 3 else [70, 64][:world], 256)]):
+            L, C, Lc = sum(rows), 3 * w, rows[rank]
+            off = [sum(rows[:r]) for r in range(world)]
+            recv, back = px.begin(G, L, C, rows, w)
+            assert recv.shape == (G, L, C) and back.shape == (G, world, Lc, w) and px.epoch == rnd + 1
+            # value of element = f(group, source rank, destination rank, row, column): checkable on the other side
+            def chunk(g, src, dst, nrows, ncols):
+                base = 1000 * g + 100 * src + 10 * dst
+                return (base + torch.arange(nrows * ncols).reshape(nrows, ncols) % 7).to(torch.bfloat16)
+            send = torch.stack([torch.stack([chunk(g, rank, d, Lc, C) for d in range(world)]) for g in range(G)])
+            px.push_in_local(send)
+            for g in range(G):
+                px.push_in(g, send[g])
+            px.wait_in(0, G - 1)
+            for g in range(G):
+                for s in range(world):
+                    ok &= bool(torch.equal(recv[g, off[s]:off[s] + rows[s]], chunk(g, s, rank, rows[s], C)))
+            # the way back: rows of rank d of my [L, w] output go to rank d's back[g, me]
+            outs = [torch.cat([chunk(g, rank, d, rows[d], w) + 1 for d in range(world)]) for g in range(G)]
+            for g in range(G):
+                px.push_out(g, outs[g])
+            px.push_out_local([(g, outs[g]) for g in range(G)])
+            px.wait_out()
+            for g in range(G):
+                for s in range(world):
+                    ok &= bool(torch.equal(back[g, s], chunk(g, s, rank, Lc, w) + 1))
+            dist.barrier()  # a forward always ends with a collective before shapes may change (peer.py invariants)
+        results[rank] = dict(ok=ok, generation=win.generation, epoch=px.epoch, capacity=win.capacity)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_exchange_rounds_ragged_and_growing(world):
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_peer_exchange_worker, args=(world, port, results), nprocs=world, join=True)
+    assert len(results) == world
+    for rank in range(world):
+        r = results[rank]
+        assert r["ok"], f"rank {rank}: exchanged bytes differ"
+        assert r["generation"] == 2 and r["epoch"] == 2, r  # the second round did not fit the first windows
